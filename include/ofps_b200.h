@@ -1,0 +1,189 @@
+/*
+ * ofps_b200.h — C ABI of libofps_b200.so, the B200 (sm_100a) hot path of h33p/ofps.
+ *
+ * This is the drop-in boundary: the entry points a Rust `cdylib` shim (one per plugin,
+ * see rust/ and INTEGRATION.md) binds with `extern "C"` to implement the reference's
+ * plugin traits.  Reference interface each group replaces (paths relative to the
+ * reference checkout):
+ *
+ *   ofpsb_block_match*          -> Decoder::process_frame            ofps/src/decoder.rs:54-59
+ *                                  (output convention of av-decoder/src/lib.rs:404-419;
+ *                                  the SAD search itself is what the H.264 encoder did
+ *                                  upstream of av-decoder — the reference has no such code)
+ *   ofpsb_densify*              -> MotionFieldDensifier::add_vector + MotionField::from
+ *                                  ofps/src/motion_field.rs:164-190, 297-308
+ *   ofpsb_detect_block_motion*  -> Detector::detect_motion           ofps/src/detection.rs:11
+ *                                  as implemented by block-motion-detector/src/lib.rs:49-119
+ *   ofpsb_almeida*              -> Estimator::estimate               ofps/src/estimator.rs:19-24
+ *                                  as implemented by almeida-estimator/src/lib.rs:100-251
+ *   ofpsb_mvec_* / ofpsb_flo_*  -> .mvec wire format motion-extract/src/main.rs:23-35,
+ *                                  motion-loader/src/lib.rs:46-65; .flo writer used by
+ *                                  flow-extract/src/main.rs:122
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Entry points without a suffix take HOST pointers and
+ *     are synchronous on return; `_dev` entry points take DEVICE pointers, enqueue on the
+ *     context's stream and return without synchronising (call ofpsb_sync()).
+ *   - Every entry point returns 0 (OFPSB_OK) or a negative OFPSB_E_* code; the message is
+ *     available through ofpsb_last_error() (thread-local).
+ *   - A context is bound to one device, may be used from any host thread, never from two
+ *     threads at once (the reference's plugin objects are Send, not Sync:
+ *     ofps/src/plugins/mod.rs:78-85).
+ *   - There is NO CPU fallback: without a usable sm_100-class GPU ofpsb_create() fails.
+ */
+#ifndef OFPS_B200_H
+#define OFPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFPSB_OK 0
+#define OFPSB_E_INVALID (-1)   /* bad argument */
+#define OFPSB_E_CUDA (-2)      /* CUDA runtime / launch failure */
+#define OFPSB_E_NOMEM (-3)     /* allocation failure */
+#define OFPSB_E_NODEVICE (-4)  /* no CUDA device / not an sm_100 part */
+#define OFPSB_E_IO (-5)        /* file I/O failure (.mvec / .flo) */
+#define OFPSB_E_CAPACITY (-6)  /* caller-provided output buffer too small */
+
+#define OFPSB_METRIC_SAD 0
+#define OFPSB_METRIC_SSD 1
+
+/* MotionEntry (ofps/src/decoder.rs:40) flattened as motion-extract writes it
+ * (motion-extract/src/main.rs:27-29): position then motion, normalised [0,1] units. */
+typedef struct { float px, py, mx, my; } ofps_mv;
+
+typedef struct ofpsb_ctx ofpsb_ctx;
+
+/* ---------------------------------------------------------------- context */
+int ofpsb_create(int device, ofpsb_ctx **out);
+void ofpsb_destroy(ofpsb_ctx *ctx);
+const char *ofpsb_last_error(void);
+const char *ofpsb_version(void);
+/* Borrow an external cudaStream_t (e.g. the caller's current stream); NULL restores the
+ * context's own non-blocking stream. */
+int ofpsb_set_stream(ofpsb_ctx *ctx, void *cuda_stream);
+int ofpsb_sync(ofpsb_ctx *ctx);
+/* sm_count, L2 bytes, total global memory bytes; any pointer may be NULL. */
+int ofpsb_device_info(ofpsb_ctx *ctx, int *sm_count, size_t *l2_bytes, size_t *mem_bytes, int *cc_major, int *cc_minor);
+/* Number of kernels launched by this context since creation (for gpu_launches accounting). */
+uint64_t ofpsb_launch_count(ofpsb_ctx *ctx);
+/* The stream the context currently enqueues on (a cudaStream_t), for event timing by the caller. */
+void *ofpsb_get_stream(ofpsb_ctx *ctx);
+/* Tuning / test knobs; unknown keys return OFPSB_E_INVALID.
+ *   "densify_path"        0 = by size (default), 1 = force the scan path, 2 = force the sort path
+ *   "block_match_kernel"  0 = tuned instance when one exists (default), 1 = force the generic kernel
+ *   "batch_chunk_pairs"   pairs per pipelined chunk in ofpsb_block_match_batch (0 = automatic) */
+int ofpsb_set_option(ofpsb_ctx *ctx, const char *key, long long value);
+
+/* Pinned host memory (page-locked; makes the batched host entry points copy asynchronously) and
+ * plain device memory helpers for callers without their own CUDA runtime binding. */
+int ofpsb_host_alloc(void **out, size_t bytes);
+void ofpsb_host_free(void *p);
+int ofpsb_dev_alloc(ofpsb_ctx *ctx, void **out, size_t bytes);
+void ofpsb_dev_free(ofpsb_ctx *ctx, void *p);
+/* Asynchronous on the context's stream (ofpsb_sync() to wait). */
+int ofpsb_copy_to_device(ofpsb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int ofpsb_copy_to_host(ofpsb_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+
+/* ----------------------------------------------------------- block matcher
+ * Exhaustive block matching of `cur` against `prev` (u8 luma, `stride` bytes per row).
+ * Blocks block x block at (bx*block, by*block) in cur, full blocks only; candidates
+ * (dx,dy) in [-range,range]^2 whose window lies fully inside prev; cost SAD or SSD;
+ * winner = lexicographic min of (cost, dx^2+dy^2, dy, dx).  Outputs, per block in raster
+ * order (any may be NULL): mv_xy[2i] = dx, mv_xy[2i+1] = dy; cost[i]; entries[i] =
+ * { pos = (block centre + (dx,dy)) * (1/W,1/H), motion = (dx,dy) * -(1/W,1/H) }.
+ * block in {4..64, multiple of 4}, range in [0,63].  *n_blocks (optional) receives the
+ * block count (w/block)*(h/block). */
+int ofpsb_block_match(ofpsb_ctx *ctx, const uint8_t *prev, const uint8_t *cur, int w, int h, int stride,
+                      int block, int range, int metric,
+                      int16_t *mv_xy, uint32_t *cost, ofps_mv *entries, size_t *n_blocks);
+
+/* Batched host entry point: n_pairs independent pairs, pair i at prev + i*pair_stride
+ * (bytes).  Outputs are n_pairs * n_blocks long.  Copies and kernels are pipelined on
+ * two streams; pinned host memory makes the copies asynchronous. */
+int ofpsb_block_match_batch(ofpsb_ctx *ctx, const uint8_t *prev, const uint8_t *cur, int w, int h, int stride,
+                            size_t pair_stride, int n_pairs, int block, int range, int metric,
+                            int16_t *mv_xy, uint32_t *cost, ofps_mv *entries, size_t *n_blocks);
+
+/* Device entry point (batched).  Output pointers are device memory, n_pairs*n_blocks. */
+int ofpsb_block_match_dev(ofpsb_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_cur, int w, int h, int stride,
+                          size_t pair_stride, int n_pairs, int block, int range, int metric,
+                          int16_t *d_mv_xy, uint32_t *d_cost, ofps_mv *d_entries);
+
+/* Device entry point for one horizontal strip of a spatially tiled frame (multi-GPU).
+ * d_cur: first row of the strip (strip_h rows, strip_h % block == 0 except for the last
+ * strip).  d_prev: the same rows of the previous frame, with halo_top valid rows stored
+ * BEFORE d_prev (negative row offsets) and halo_bottom valid rows after the strip.
+ * y_offset / full_h place the strip in the whole frame (entries are normalised by full_h;
+ * a candidate is legal iff its window lies inside [y_offset-halo_top,
+ * y_offset+strip_h+halo_bottom), which equals the whole-frame rule when the halos are
+ * min(range, rows available)). */
+int ofpsb_block_match_strip_dev(ofpsb_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_cur, int w, int strip_h,
+                                int stride, int halo_top, int halo_bottom, int y_offset, int full_h,
+                                int block, int range, int metric,
+                                int16_t *d_mv_xy, uint32_t *d_cost, ofps_mv *d_entries);
+
+/* -------------------------------------------------------------- densifier
+ * field_xy: gw*gh*2 floats, cell-major [x0,y0,x1,y1,...], cell = y*gw+x
+ * (MotionField::as_slice, ofps/src/motion_field.rs:42-49).  counts (optional): same
+ * shape, the densifier's count rows.  Bit-exact with the reference order of additions. */
+int ofpsb_densify(ofpsb_ctx *ctx, const ofps_mv *entries, size_t n, size_t gw, size_t gh,
+                  float *field_xy, float *counts);
+int ofpsb_densify_dev(ofpsb_ctx *ctx, const ofps_mv *d_entries, size_t n, size_t gw, size_t gh,
+                      float *d_field_xy, float *d_counts);
+
+/* --------------------------------------------------------------- detector
+ * BlockMotionDetection::detect_motion.  *has_motion = 1 for Some, 0 for None; *area =
+ * cell count of the winning island (0 when None); *dim = block_dim; field_xy receives
+ * dim*dim*2 floats (zeros when None) and must hold field_cap_cells cells
+ * (OFPSB_E_CAPACITY otherwise; *dim is still written). */
+int ofpsb_block_dim(float min_size, size_t subdivide, size_t *dim);
+int ofpsb_detect_block_motion(ofpsb_ctx *ctx, const ofps_mv *entries, size_t n,
+                              float min_size, size_t subdivide, float target_motion,
+                              int *has_motion, size_t *area, size_t *dim,
+                              float *field_xy, size_t field_cap_cells);
+/* entries in device memory; results still returned to host (synchronous). */
+int ofpsb_detect_block_motion_dev(ofpsb_ctx *ctx, const ofps_mv *d_entries, size_t n,
+                                  float min_size, size_t subdivide, float target_motion,
+                                  int *has_motion, size_t *area, size_t *dim,
+                                  float *field_xy, size_t field_cap_cells);
+
+/* -------------------------------------------------------------- estimator
+ * AlmeidaEstimator::estimate.  Camera passed as (aspect, fov_y_deg) — recoverable from
+ * StandardCamera::aspect_ratio() and fov().1 (ofps/src/camera.rs:166-177).
+ * use_ransac = 0: solve_ypr_given; 1: solve_ypr_ransac with the seeded counter RNG
+ * documented in DESIGN.md (the reference's thread_rng is not reproducible).
+ * quat_wijk: rotation as (w,i,j,k); translation is always zero in the reference. */
+int ofpsb_almeida(ofpsb_ctx *ctx, const ofps_mv *entries, size_t n, float aspect, float fov_y_deg,
+                  int use_ransac, size_t num_iters, float inlier_angle_deg, size_t ransac_samples,
+                  uint64_t seed, float quat_wijk[4]);
+int ofpsb_almeida_dev(ofpsb_ctx *ctx, const ofps_mv *d_entries, size_t n, float aspect, float fov_y_deg,
+                      int use_ransac, size_t num_iters, float inlier_angle_deg, size_t ransac_samples,
+                      uint64_t seed, float quat_wijk[4]);
+
+/* --------------------------------------------------- fused per-frame paths
+ * Detection-tab frame (ofps-suite/src/app/detection.rs:92-168): frame pair -> motion
+ * vectors -> detector, one call, intermediates stay in HBM.  entries (optional, host)
+ * receives the n_blocks motion entries. */
+int ofpsb_frame_detect(ofpsb_ctx *ctx, const uint8_t *prev, const uint8_t *cur, int w, int h, int stride,
+                       int block, int range, int metric,
+                       float min_size, size_t subdivide, float target_motion,
+                       ofps_mv *entries, size_t *n_blocks,
+                       int *has_motion, size_t *area, size_t *dim, float *field_xy, size_t field_cap_cells);
+
+/* ------------------------------------------------------ interchange files
+ * .mvec: per frame u32 LE count, then count x 4 f32 LE (motion-extract/src/main.rs:23-35). */
+int ofpsb_mvec_append(const char *path, const ofps_mv *entries, size_t n, int truncate);
+/* Reads frame `frame_index`; *n receives its entry count; entries may be NULL to query. */
+int ofpsb_mvec_read(const char *path, size_t frame_index, ofps_mv *entries, size_t cap, size_t *n);
+/* Middlebury .flo ("PIEH", w, h, then w*h*2 f32), as OpenCV's writeOpticalFlow emits. */
+int ofpsb_flo_write(const char *path, const float *field_xy, size_t w, size_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFPS_B200_H */

@@ -1,0 +1,598 @@
+// K5 / K6: AlmeidaEstimator — iterated 3-parameter least-squares camera rotation fit
+// (almeida-estimator/src/lib.rs:123-200, solve_ypr_given) and its RANSAC wrapper (:202-251),
+// over StandardCamera::delta / point_angle (ofps/src/camera.rs:45-117, 120-161).
+//
+// Arithmetic contract.  Everything that happens PER ENTRY (un-project, rotate, project, the
+// divide by NDC z, the four deltas, the twelve products) is evaluated in f32 in the reference's
+// operation order with no FMA contraction (the library is built with --fmad=false), i.e. the
+// per-entry terms are the ones the CPU restatement produces.  What differs is the REDUCTION:
+// the reference folds N terms sequentially in f32 (almeida:126-130); here each thread
+// accumulates its terms in f64, blocks combine in a fixed order, and the 3x3 system is rounded
+// to f32 before the reference's f32 LU.  That is deterministic (independent of block scheduling)
+// and closer to the exact sum than the sequential fold, so the quaternion is compared with a
+// tolerance (1e-4, see tests) instead of bit-for-bit.
+//
+// Work saving that does not change results: the three prototype fields (roll/pitch/yaw deltas,
+// almeida:30-47, 151-153) do not depend on the iteration, so the 3x3 normal matrix A is
+// accumulated once, and later iterations only accumulate the right-hand side b.
+//
+// Camera matrices and the prototype rotations are built on the host in f32 (tanf/sinf/cosf of
+// the host libm, as the CPU path does) and passed by value.
+#include "common.cuh"
+
+#include <cmath>
+
+namespace ofpsb {
+
+namespace {
+
+constexpr int LSQ_NT = 256;
+constexpr int LSQ_ITERS = 30;          // ceil(15 / ALPHA), almeida:132
+constexpr float ALPHA = 0.5f;          // almeida:18
+
+struct AlmeidaConst {
+    float unproj[16];   // view^T * inv_proj, row-major (camera.rs:54 with rotate()'s view, :91-96)
+    float proj[4];      // m00, m11, m22, m23 of Perspective3
+    float roll[9], pitch[9], yaw[9];   // 3x3 parts of the prototype rotations (almeida:33,37,41)
+    float fx, fy;       // intrinsics focal lengths (camera.rs:120-129)
+    float eps_r;        // EPS = 0.001 deg in radians (almeida:17)
+};
+
+struct AlmeidaState {
+    float rotation[4];   // running estimate (w,i,j,k)
+    float a[9];          // normal matrix, accumulated at iteration 0
+    unsigned int ticket;
+    unsigned int pad;
+};
+
+// ---- camera (f32, reference operation order; see oracle/camera_almeida.inc)
+__device__ __forceinline__ void unproject_world(const AlmeidaConst& c, float x, float y, float w[3])
+{
+    const float p0 = x * 2.0f - 1.0f, p1 = y * 2.0f - 1.0f, p2 = 1.0f;
+    const float* m = c.unproj;
+    float t[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float acc = m[i * 4 + 0] * p0;
+        acc = acc + m[i * 4 + 1] * p1;
+        acc = acc + m[i * 4 + 2] * p2;
+        t[i] = acc + m[i * 4 + 3];
+    }
+    float n = (m[12] * p0 + m[13] * p1) + m[14] * p2;
+    n = n + m[15];
+    if (n != 0.0f) {
+        w[0] = t[0] / n; w[1] = t[1] / n; w[2] = t[2] / n;
+    } else {
+        w[0] = t[0]; w[1] = t[1]; w[2] = t[2];
+    }
+}
+
+// rotate the world point by a pure rotation (homogeneous last row 0,0,0,1 -> divide by 1), apply
+// rotate()'s fixed view, project, divide by NDC z, back to [0,1], subtract the start (camera.rs:72-117)
+__device__ __forceinline__ void delta_from_world(const AlmeidaConst& c, const float w[3], const float* r, float x,
+                                                 float y, float out[2])
+{
+    float rw[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float acc = r[i * 3 + 0] * w[0];
+        acc = acc + r[i * 3 + 1] * w[1];
+        acc = acc + r[i * 3 + 2] * w[2];
+        rw[i] = acc + 0.0f;
+    }
+    const float v0 = -rw[0], v1 = rw[2], v2 = rw[1];     // view = rows (-1,0,0),(0,0,1),(0,1,0)
+    const float inv_denom = -1.0f / v2;
+    const float sx = c.proj[0] * v0 * inv_denom;
+    const float sy = c.proj[1] * v1 * inv_denom;
+    const float sz = (c.proj[2] * v2 + c.proj[3]) * inv_denom;
+    const float qx = sx / sz, qy = sy / sz;
+    out[0] = (qx + 1.0f) * 0.5f - x;
+    out[1] = (qy + 1.0f) * 0.5f - y;
+}
+
+__device__ __forceinline__ void quat_to_mat3(const float q[4], float m[9])
+{
+    const float w = q[0], i = q[1], j = q[2], k = q[3];
+    const float ww = w * w, ii = i * i, jj = j * j, kk = k * k;
+    const float ij = i * j * 2.0f, wk = w * k * 2.0f, wj = w * j * 2.0f;
+    const float ik = i * k * 2.0f, jk = j * k * 2.0f, wi = w * i * 2.0f;
+    m[0] = ww + ii - jj - kk; m[1] = ij - wk;           m[2] = wj + ik;
+    m[3] = wk + ij;           m[4] = ww - ii + jj - kk; m[5] = jk - wi;
+    m[6] = ik - wj;           m[7] = wi + jk;           m[8] = ww - ii - jj + kk;
+}
+
+__device__ __forceinline__ void quat_from_euler(float roll, float pitch, float yaw, float q[4])
+{
+    const float sr = sinf(roll * 0.5f), cr = cosf(roll * 0.5f);
+    const float sp = sinf(pitch * 0.5f), cp = cosf(pitch * 0.5f);
+    const float sy = sinf(yaw * 0.5f), cy = cosf(yaw * 0.5f);
+    q[0] = cr * cp * cy + sr * sp * sy;
+    q[1] = sr * cp * cy - cr * sp * sy;
+    q[2] = cr * sp * cy + sr * cp * sy;
+    q[3] = cr * cp * sy - sr * sp * cy;
+}
+
+__device__ __forceinline__ void quat_mul(const float a[4], const float b[4], float o[4])
+{
+    const float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    const float i = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    const float j = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+    const float k = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+    o[0] = w; o[1] = i; o[2] = j; o[3] = k;
+}
+
+// Matrix3::lu() with partial pivoting + solve; false when a pivot is zero (almeida:181-183)
+__device__ bool lu3_solve(const float a_in[9], const float b_in[3], float x[3])
+{
+    float a[9], b[3];
+    for (int i = 0; i < 9; i++) a[i] = a_in[i];
+    for (int i = 0; i < 3; i++) b[i] = b_in[i];
+    int perm[3] = {0, 1, 2};
+    for (int i = 0; i < 3; i++) {
+        int piv = i;
+        float best = fabsf(a[i * 3 + i]);
+        for (int r = i + 1; r < 3; r++) {
+            const float v = fabsf(a[r * 3 + i]);
+            if (v > best) { best = v; piv = r; }
+        }
+        if (a[piv * 3 + i] == 0.0f) continue;
+        if (piv != i) {
+            for (int c = 0; c < 3; c++) { const float t = a[i * 3 + c]; a[i * 3 + c] = a[piv * 3 + c]; a[piv * 3 + c] = t; }
+            const int t = perm[i]; perm[i] = perm[piv]; perm[piv] = t;
+        }
+        const float inv_diag = 1.0f / a[i * 3 + i];
+        for (int r = i + 1; r < 3; r++) a[r * 3 + i] = a[r * 3 + i] * inv_diag;
+        for (int c = i + 1; c < 3; c++) {
+            const float pr = a[i * 3 + c];
+            for (int r = i + 1; r < 3; r++) a[r * 3 + c] = a[r * 3 + c] + (-pr) * a[r * 3 + i];
+        }
+    }
+    float y[3] = {b[perm[0]], b[perm[1]], b[perm[2]]};
+    for (int i = 0; i < 2; i++) {
+        const float coeff = y[i];
+        for (int r = i + 1; r < 3; r++) y[r] = y[r] + (-coeff) * a[r * 3 + i];
+    }
+    for (int i = 2; i >= 0; i--) {
+        const float d = a[i * 3 + i];
+        if (d == 0.0f) return false;
+        y[i] = y[i] / d;
+        for (int r = 0; r < i; r++) y[r] = y[r] + (-y[i]) * a[r * 3 + i];
+    }
+    x[0] = y[0]; x[1] = y[1]; x[2] = y[2];
+    return true;
+}
+
+// one solver step from the reduced system (almeida:181-195)
+__device__ void lsq_step(const float a[9], const float b[3], float eps_r, int it, float rotation[4])
+{
+    const float alpha = (it == LSQ_ITERS - 1) ? 1.0f : ALPHA;   // almeida:138
+    float model[3];
+    if (!lu3_solve(a, b, model)) model[0] = model[1] = model[2] = 0.0f;
+    for (int k = 0; k < 3; k++) model[k] = model[k] * eps_r * alpha;
+    float roll[4], pitch[4], yaw[4], pr[4], rot[4], nr[4];
+    quat_from_euler(0.0f, model[0], 0.0f, roll);
+    quat_from_euler(model[1], 0.0f, 0.0f, pitch);
+    quat_from_euler(0.0f, 0.0f, -model[2], yaw);
+    quat_mul(pitch, roll, pr);
+    quat_mul(pr, yaw, rot);
+    quat_mul(rotation, rot, nr);
+    for (int k = 0; k < 4; k++) rotation[k] = nr[k];
+}
+
+// the four vectors of one entry (almeida:142-157)
+__device__ __forceinline__ void entry_vectors(const AlmeidaConst& c, const float4 e, const float rotm[9], bool protos,
+                                              float v[4][2])
+{
+    float w[3], d[2];
+    unproject_world(c, e.x, e.y, w);
+    delta_from_world(c, w, rotm, e.x, e.y, d);
+    v[0][0] = e.z - d[0];
+    v[0][1] = e.w - d[1];
+    delta_from_world(c, w, c.roll, e.x, e.y, v[1]);
+    delta_from_world(c, w, c.pitch, e.x, e.y, v[2]);
+    delta_from_world(c, w, c.yaw, e.x, e.y, v[3]);
+    (void)protos;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------ least-squares kernel
+// SINGLE: one CTA runs all 30 iterations (small inputs: RANSAC refits, the reference's <= 12,600
+// vector fields).  Otherwise one launch per iteration over a fixed grid; per-block f64 partials
+// are combined by the last block to arrive, in block order.
+template <bool SINGLE>
+__global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __restrict__ entries,
+                                                             const uint32_t* __restrict__ idx, size_t n_arg,
+                                                             const uint32_t* __restrict__ n_ptr, const AlmeidaConst cst,
+                                                             AlmeidaState* __restrict__ state,
+                                                             double* __restrict__ partial, float* __restrict__ out_quat,
+                                                             int it_arg)
+{
+    __shared__ double red[LSQ_NT / 32][12];
+    __shared__ float s_rot[4];
+    __shared__ float s_a[9];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    const size_t n = n_ptr ? (size_t)*n_ptr : n_arg;
+    const float4* e4 = reinterpret_cast<const float4*>(entries);
+
+    if (n_ptr && n < 3) {   // solve_ypr_ransac: fewer than 3 inliers -> identity (almeida:246-250)
+        if (blockIdx.x == 0 && tid == 0 && (SINGLE || it_arg == LSQ_ITERS - 1)) {
+            out_quat[0] = 1.0f; out_quat[1] = 0.0f; out_quat[2] = 0.0f; out_quat[3] = 0.0f;
+        }
+        return;
+    }
+    if (tid < 4) s_rot[tid] = SINGLE ? (tid == 0 ? 1.0f : 0.0f) : (it_arg == 0 ? (tid == 0 ? 1.0f : 0.0f) : state->rotation[tid]);
+    if (!SINGLE && it_arg > 0 && tid < 9) s_a[tid] = state->a[tid];
+    __syncthreads();
+
+    const int it_begin = SINGLE ? 0 : it_arg;
+    const int it_end = SINGLE ? LSQ_ITERS : it_arg + 1;
+    for (int it = it_begin; it < it_end; it++) {
+        float rot[4] = {s_rot[0], s_rot[1], s_rot[2], s_rot[3]};
+        float rotm[9];
+        quat_to_mat3(rot, rotm);
+        const bool first = it == 0;
+        double acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) acc[k] = 0.0;
+        for (size_t i = (size_t)blockIdx.x * LSQ_NT + tid; i < n; i += (size_t)gridDim.x * LSQ_NT) {
+            const float4 e = __ldg(e4 + (idx ? idx[i] : i));
+            float v[4][2];
+            entry_vectors(cst, e, rotm, first, v);
+            if (first) {
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        acc[r * 3 + c] += (double)(v[r + 1][0] * v[c + 1][0] + v[r + 1][1] * v[c + 1][1]);
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++) acc[9 + r] += (double)(v[r + 1][0] * v[0][0] + v[r + 1][1] * v[0][1]);
+        }
+        // block reduction (fixed order: lanes by shuffle tree, warps sequentially)
+        const int k0 = first ? 0 : 9;
+        for (int k = k0; k < 12; k++) {
+            const double s = warp_sum(acc[k]);
+            if ((tid & 31) == 0) red[tid >> 5][k] = s;
+        }
+        __syncthreads();
+        if (SINGLE) {
+            if (tid == 0) {
+                float a[9], b[3];
+                for (int k = 0; k < 12; k++) {
+                    if (k < k0) continue;
+                    double s = 0.0;
+                    for (int w = 0; w < LSQ_NT / 32; w++) s += red[w][k];
+                    if (k < 9) s_a[k] = (float)s;
+                    else b[k - 9] = (float)s;
+                }
+                for (int k = 0; k < 9; k++) a[k] = s_a[k];
+                float r4[4] = {s_rot[0], s_rot[1], s_rot[2], s_rot[3]};
+                lsq_step(a, b, cst.eps_r, it, r4);
+                for (int k = 0; k < 4; k++) s_rot[k] = r4[k];
+            }
+            __syncthreads();
+        } else {
+            if (tid < 12 && tid >= k0) {
+                double s = 0.0;
+                for (int w = 0; w < LSQ_NT / 32; w++) s += red[w][tid];
+                partial[(size_t)blockIdx.x * 12 + tid] = s;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned t = atomicAdd(&state->ticket, 1u);
+                s_last = t == gridDim.x - 1;
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                if (tid < 12 && tid >= k0) {
+                    double s = 0.0;
+                    for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(&partial[(size_t)b * 12 + tid]);
+                    red[0][tid] = s;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    float a[9], b[3];
+                    for (int k = 0; k < 9; k++) a[k] = first ? (float)red[0][k] : s_a[k];
+                    for (int k = 0; k < 3; k++) b[k] = (float)red[0][9 + k];
+                    float r4[4] = {s_rot[0], s_rot[1], s_rot[2], s_rot[3]};
+                    lsq_step(a, b, cst.eps_r, it, r4);
+                    for (int k = 0; k < 4; k++) { state->rotation[k] = r4[k]; s_rot[k] = r4[k]; }
+                    if (first) for (int k = 0; k < 9; k++) state->a[k] = a[k];
+                    state->ticket = 0;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    // rotation.inverse() (almeida:199)
+    if ((SINGLE || (s_last && it_arg == LSQ_ITERS - 1)) && tid == 0) {
+        out_quat[0] = s_rot[0]; out_quat[1] = -s_rot[1]; out_quat[2] = -s_rot[2]; out_quat[3] = -s_rot[3];
+    }
+}
+
+// ------------------------------------------------------------------ seeded sampling (K6)
+// Same keyed permutation as oracle/ofps_oracle.c (orc_perm_index): 4-round balanced Feistel with
+// cycle walking, round function splitmix64.  Stands in for rand::thread_rng +
+// SliceRandom::choose_multiple (almeida:212-222), which are not reproducible.
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__device__ unsigned long long perm_index(unsigned long long seed, unsigned long long iter, unsigned long long stream,
+                                         unsigned long long j, unsigned long long n)
+{
+    if (n <= 1) return 0;
+    unsigned bits = 0;
+    while (((unsigned long long)1 << bits) < n) bits++;
+    unsigned hb = (bits + 1) / 2;
+    if (hb == 0) hb = 1;
+    const unsigned long long mask = ((unsigned long long)1 << hb) - 1;
+    const unsigned long long key = splitmix64(seed ^ splitmix64(iter * 2 + stream + 0x0F95B200ull));
+    unsigned long long v = j;
+    do {
+        unsigned long long l = (v >> hb) & mask, r = v & mask;
+        for (unsigned round = 0; round < 4; round++) {
+            const unsigned long long f = splitmix64(key + ((unsigned long long)round << 32) + r) & mask;
+            const unsigned long long nl = r, nr = l ^ f;
+            l = nl; r = nr;
+        }
+        v = (l << hb) | r;
+    } while (v >= n);
+    return v;
+}
+
+// inlier test of one entry under hypothesis matrix `mat` (almeida:226-239)
+__device__ __forceinline__ bool is_inlier(const AlmeidaConst& c, const float4 e, const float mat[9], float target_sq)
+{
+    float w[3], d[2];
+    unproject_world(c, e.x, e.y, w);
+    delta_from_world(c, w, mat, e.x, e.y, d);
+    const float sx = e.x + d[0], sy = e.y + d[1];
+    const float vx = e.z - d[0], vy = e.w - d[1];
+    const float ax = atanf((sx - 0.5f) / c.fx), ay = atanf((sy - 0.5f) / c.fy);   // point_angle
+    const float cx = vx * cosf(ax), cy = vy * cosf(ay);
+    return cx * cx + cy * cy <= target_sq;
+}
+
+constexpr int RS_NT = 128;
+
+// One CTA per RANSAC iteration: 3-sample fit by one thread in the reference's sequential order,
+// then all threads score the iteration's sample subset.
+__global__ void __launch_bounds__(RS_NT) ransac_hypothesis_kernel(const ofps_mv* __restrict__ entries, size_t n,
+                                                                  const AlmeidaConst cst, unsigned long long seed,
+                                                                  size_t k_samples, float target_sq,
+                                                                  float* __restrict__ fits, uint32_t* __restrict__ counts)
+{
+    __shared__ float s_mat[9];
+    __shared__ unsigned s_cnt;
+    const int tid = threadIdx.x;
+    const unsigned long long it = blockIdx.x;
+    const float4* e4 = reinterpret_cast<const float4*>(entries);
+    if (tid == 0) {
+        s_cnt = 0;
+        const int s3 = n < 3 ? (int)n : 3;
+        float4 smp[3];
+        for (int j = 0; j < s3; j++) smp[j] = __ldg(e4 + perm_index(seed, it, 0, j, n));
+        float rotation[4] = {1.0f, 0.0f, 0.0f, 0.0f};
+        float a[9];
+        for (int iter = 0; iter < LSQ_ITERS; iter++) {
+            float rotm[9], b[3] = {0.0f, 0.0f, 0.0f};
+            quat_to_mat3(rotation, rotm);
+            if (iter == 0) for (int k = 0; k < 9; k++) a[k] = 0.0f;
+            for (int j = 0; j < s3; j++) {
+                float v[4][2];
+                entry_vectors(cst, smp[j], rotm, iter == 0, v);
+                if (iter == 0)
+                    for (int r = 0; r < 3; r++)
+                        for (int c = 0; c < 3; c++)
+                            a[r * 3 + c] = a[r * 3 + c] + (v[r + 1][0] * v[c + 1][0] + v[r + 1][1] * v[c + 1][1]);
+                for (int r = 0; r < 3; r++) b[r] = b[r] + (v[r + 1][0] * v[0][0] + v[r + 1][1] * v[0][1]);
+            }
+            lsq_step(a, b, cst.eps_r, iter, rotation);
+        }
+        // fit = rotation.inverse(); mat = fit.inverse().to_homogeneous() (almeida:199, 224)
+        const float fit[4] = {rotation[0], -rotation[1], -rotation[2], -rotation[3]};
+        const float inv[4] = {fit[0], -fit[1], -fit[2], -fit[3]};
+        float m[9];
+        quat_to_mat3(inv, m);
+        for (int k = 0; k < 9; k++) s_mat[k] = m[k];
+        for (int k = 0; k < 4; k++) fits[it * 4 + k] = fit[k];
+    }
+    __syncthreads();
+    float mat[9];
+    for (int k = 0; k < 9; k++) mat[k] = s_mat[k];
+    unsigned local = 0;
+    for (size_t j = tid; j < k_samples; j += RS_NT) {
+        const float4 e = __ldg(e4 + perm_index(seed, it, 1, j, n));
+        local += is_inlier(cst, e, mat, target_sq) ? 1u : 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((tid & 31) == 0) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (tid == 0) counts[it] = s_cnt;
+}
+
+constexpr int SEL_NT = 1024;
+
+// Pick the iteration with the most inliers (strictly greater wins -> earliest on ties,
+// almeida:241-243) and rebuild its inlier list in sample order.
+__global__ void __launch_bounds__(SEL_NT) ransac_select_kernel(const ofps_mv* __restrict__ entries, size_t n,
+                                                               const AlmeidaConst cst, unsigned long long seed,
+                                                               size_t k_samples, float target_sq, size_t num_iters,
+                                                               const float* __restrict__ fits,
+                                                               const uint32_t* __restrict__ counts,
+                                                               uint32_t* __restrict__ inlier_idx,
+                                                               uint32_t* __restrict__ result /* [count, iter] */)
+{
+    __shared__ unsigned long long s_best;
+    __shared__ float s_mat[9];
+    __shared__ unsigned s_warp[SEL_NT / 32];
+    __shared__ unsigned s_base;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_best = 0ull; s_base = 0; }
+    __syncthreads();
+    for (size_t i = tid; i < num_iters; i += SEL_NT)
+        atomicMax(&s_best, ((unsigned long long)counts[i] << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i));
+    __syncthreads();
+    const uint32_t best_cnt = (uint32_t)(s_best >> 32);
+    const uint32_t best_it = 0xFFFFFFFFu - (uint32_t)(s_best & 0xFFFFFFFFull);
+    if (tid == 0) {
+        result[0] = best_cnt;
+        result[1] = best_cnt ? best_it : 0u;
+        const float* fit = fits + (size_t)best_it * 4;
+        const float inv[4] = {fit[0], -fit[1], -fit[2], -fit[3]};
+        float m[9];
+        quat_to_mat3(inv, m);
+        for (int k = 0; k < 9; k++) s_mat[k] = m[k];
+    }
+    __syncthreads();
+    if (best_cnt == 0) return;
+    float mat[9];
+    for (int k = 0; k < 9; k++) mat[k] = s_mat[k];
+    const float4* e4 = reinterpret_cast<const float4*>(entries);
+    for (size_t base = 0; base < k_samples; base += SEL_NT) {
+        const size_t j = base + tid;
+        uint32_t e_idx = 0;
+        bool in = false;
+        if (j < k_samples) {
+            e_idx = (uint32_t)perm_index(seed, best_it, 1, j, n);
+            in = is_inlier(cst, __ldg(e4 + e_idx), mat, target_sq);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(bal);
+        __syncthreads();
+        unsigned off = s_base;
+        for (int w = 0; w < (tid >> 5); w++) off += s_warp[w];
+        if (in) inlier_idx[off + __popc(bal & ((1u << (tid & 31)) - 1u))] = e_idx;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned tot = 0;
+            for (int w = 0; w < SEL_NT / 32; w++) tot += s_warp[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+}
+
+void mat3_from_euler_host(float roll, float pitch, float yaw, float m[9])
+{
+    // Rotation3::from_euler_angles(roll, pitch, yaw) = Rz(yaw) Ry(pitch) Rx(roll)
+    const float sr = sinf(roll), cr = cosf(roll);
+    const float sp = sinf(pitch), cp = cosf(pitch);
+    const float sy = sinf(yaw), cy = cosf(yaw);
+    m[0] = cy * cp; m[1] = cy * sp * sr - sy * cr; m[2] = cy * sp * cr + sy * sr;
+    m[3] = sy * cp; m[4] = sy * sp * sr + cy * cr; m[5] = sy * sp * cr - cy * sr;
+    m[6] = -sp;     m[7] = cp * sr;                m[8] = cp * cr;
+}
+
+void make_const(float aspect, float fov_y_deg, AlmeidaConst& c)
+{
+    // StandardCamera::new (camera.rs:26-35): Perspective3::new(aspect, fovy, 0.1, 10) and its inverse
+    const float DEG2RAD = 0.017453292519943295f;
+    const float znear = 0.1f, zfar = 10.0f;
+    const float fovy = fov_y_deg * DEG2RAD;
+    const float m11 = 1.0f / tanf(fovy / 2.0f);
+    const float m00 = m11 / aspect;
+    const float m22 = (zfar + znear) / (znear - zfar);
+    const float m23 = zfar * znear * 2.0f / (znear - zfar);
+    c.proj[0] = m00; c.proj[1] = m11; c.proj[2] = m22; c.proj[3] = m23;
+    float ip[16] = {0};
+    const float m32 = -1.0f;
+    ip[0] = 1.0f / m00;
+    ip[5] = 1.0f / m11;
+    ip[10] = 0.0f;
+    ip[11] = 1.0f / m32;
+    ip[14] = 1.0f / m23;
+    ip[15] = -m22 / (m23 * m32);
+    static const float view_t[16] = {-1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
+    for (int j = 0; j < 4; j++)       // nalgebra gemm order: first column scaled, the rest axpy'd
+        for (int i = 0; i < 4; i++) {
+            float acc = view_t[i * 4 + 0] * ip[0 * 4 + j];
+            for (int k = 1; k < 4; k++) acc = acc + view_t[i * 4 + k] * ip[k * 4 + j];
+            c.unproj[i * 4 + j] = acc;
+        }
+    const float PI_F = 3.14159265358979323846f;
+    c.eps_r = 0.001f * PI_F / 180.0f;                       // almeida:17
+    mat3_from_euler_host(0.0f, c.eps_r, 0.0f, c.roll);      // almeida:33
+    mat3_from_euler_host(c.eps_r, 0.0f, 0.0f, c.pitch);     // almeida:37
+    mat3_from_euler_host(0.0f, 0.0f, -c.eps_r, c.yaw);      // almeida:41
+    c.fy = 0.5f / tanf((fov_y_deg * DEG2RAD) / 2.0f);       // camera.rs:120-129
+    c.fx = c.fy / aspect;
+}
+
+constexpr size_t SINGLE_MAX = 16384;   // entries handled by the one-CTA solver
+
+int run_lsq(const ofps_mv* d_entries, const uint32_t* d_idx, size_t n, const uint32_t* d_n_ptr, const AlmeidaConst& cst,
+            float* d_quat, AlmeidaScratch& s, int sm_count, cudaStream_t stream, uint64_t* launches)
+{
+    if (int rc = s.state.reserve(sizeof(AlmeidaState))) return rc;
+    AlmeidaState* st = s.state.as<AlmeidaState>();
+    if (n <= SINGLE_MAX) {
+        almeida_lsq_kernel<true><<<1, LSQ_NT, 0, stream>>>(d_entries, d_idx, n, d_n_ptr, cst, st, nullptr, d_quat, 0);
+        OFPSB_CUDA_TRY(cudaGetLastError());
+        if (launches) ++*launches;
+        return OFPSB_OK;
+    }
+    size_t want = (n + (size_t)LSQ_NT * 4 - 1) / ((size_t)LSQ_NT * 4);
+    const size_t cap = (size_t)(sm_count > 0 ? sm_count : 148) * 8;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (int rc = s.partial.reserve((size_t)grid * 12 * sizeof(double))) return rc;
+    OFPSB_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(AlmeidaState), stream));
+    for (int it = 0; it < LSQ_ITERS; it++)
+        almeida_lsq_kernel<false><<<grid, LSQ_NT, 0, stream>>>(d_entries, d_idx, n, d_n_ptr, cst, st,
+                                                               s.partial.as<double>(), d_quat, it);
+    OFPSB_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += LSQ_ITERS;
+    return OFPSB_OK;
+}
+
+}  // namespace
+
+int launch_almeida(const ofps_mv* d_entries, size_t n, float aspect, float fov_y_deg, int use_ransac, size_t num_iters,
+                   float inlier_angle_deg, size_t ransac_samples, uint64_t seed, float* d_quat, AlmeidaScratch& s,
+                   int sm_count, cudaStream_t stream, uint64_t* launches)
+{
+    if (n > 0xFFFFFFF0ull) {
+        set_error("almeida: too many entries (%zu)", n);
+        return OFPSB_E_INVALID;
+    }
+    AlmeidaConst cst;
+    make_const(aspect, fov_y_deg, cst);
+    if (!use_ransac) return run_lsq(d_entries, nullptr, n, nullptr, cst, d_quat, s, sm_count, stream, launches);
+
+    if (num_iters == 0 || num_iters > 1000000) {
+        set_error("almeida: ransac iterations %zu out of range", num_iters);
+        return OFPSB_E_INVALID;
+    }
+    const size_t k = ransac_samples < n ? ransac_samples : n;
+    const float target = inlier_angle_deg * 0.017453292519943295f;   // almeida:210
+    const float target_sq = target * target;
+    if (int rc = s.hyp.reserve(num_iters * 4 * sizeof(float) + num_iters * sizeof(uint32_t))) return rc;
+    if (int rc = s.inlier_idx.reserve((k ? k : 1) * sizeof(uint32_t))) return rc;
+    if (int rc = s.flags.reserve(2 * sizeof(uint32_t))) return rc;
+    float* fits = s.hyp.as<float>();
+    uint32_t* counts = reinterpret_cast<uint32_t*>(fits + num_iters * 4);
+    uint32_t* result = s.flags.as<uint32_t>();
+    ransac_hypothesis_kernel<<<(unsigned)num_iters, RS_NT, 0, stream>>>(d_entries, n, cst, seed, k, target_sq, fits, counts);
+    ransac_select_kernel<<<1, SEL_NT, 0, stream>>>(d_entries, n, cst, seed, k, target_sq, num_iters, fits, counts,
+                                                   s.inlier_idx.as<uint32_t>(), result);
+    OFPSB_CUDA_TRY(cudaGetLastError());
+    if (launches) *launches += 2;
+    // refit on the best inlier set; the count lives on the device (result[0])
+    return run_lsq(d_entries, s.inlier_idx.as<uint32_t>(), k, result, cst, d_quat, s, sm_count, stream, launches);
+}
+
+}  // namespace ofpsb

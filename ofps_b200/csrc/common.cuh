@@ -1,0 +1,123 @@
+// Internal declarations shared by the kernels and the C ABI (api.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstddef>
+#include <vector>
+
+#include "../../include/ofps_b200.h"
+
+namespace ofpsb {
+
+void set_error(const char* fmt, ...);
+
+#define OFPSB_CUDA_TRY(expr)                                                                      \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ::ofpsb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                               __LINE__);                                                         \
+            return OFPSB_E_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+// Growable device scratch buffer owned by a context.
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+// Growable pinned host buffer.
+struct PinBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+// ---------------------------------------------------------------------------- block matcher
+struct BlockMatchParams {
+    const uint8_t* prev;   // row 0 = the row of the previous frame aligned with cur row 0
+    const uint8_t* cur;    // row 0 of the strip / frame
+    int w;                 // frame width in pixels
+    int strip_h;           // rows of cur handled by this launch
+    int stride;            // bytes per row (both planes)
+    long long pair_stride; // bytes between consecutive pairs (batched launches)
+    int n_pairs;
+    int halo_top, halo_bottom;  // valid prev rows before row 0 / after row strip_h-1
+    int y_offset, full_h;       // position of the strip in the whole frame
+    int block, range, metric;
+    int nbx, nby;               // full blocks in this launch
+    int16_t* mv_xy;             // [n_pairs][nby*nbx][2] or null
+    uint32_t* cost;             // [n_pairs][nby*nbx] or null
+    ofps_mv* entries;           // [n_pairs][nby*nbx] or null
+};
+
+// Launches the block matcher (tuned template instance if one exists for (block, range),
+// otherwise the generic kernel).  Returns 0 or OFPSB_E_*; *launches += kernels launched.
+int launch_block_match(const BlockMatchParams& p, cudaStream_t stream, uint64_t* launches);
+// Forces the generic (untuned) kernel; used by tests to cross-check the tuned instances.
+int launch_block_match_generic(const BlockMatchParams& p, cudaStream_t stream, uint64_t* launches);
+
+// ---------------------------------------------------------------------------- densify / detect
+struct DensifyScratch {
+    DevBuf keys_a, keys_b, vals_a, vals_b, hist, cell_start, sums;
+};
+
+// entries (device) -> field (device, gw*gh*2) [+ counts]; bit-exact reference order.
+// force_path: 0 = choose by size, 1 = scan path, 2 = sort path (tests cross-check both).
+int launch_densify(const ofps_mv* d_entries, size_t n, size_t gw, size_t gh, float* d_field, float* d_counts,
+                   DensifyScratch& scratch, cudaStream_t stream, uint64_t* launches, int force_path = 0);
+
+struct DetectResult {   // written by the detector kernel (device), copied to host
+    unsigned long long best_key;
+    unsigned int area;
+    unsigned int seed_cell;
+    int has_motion;
+    int pad;
+};
+
+// mean field (device, dim*dim*2) -> island field (device) + result record.
+int launch_detect(const float* d_mean_field, size_t dim, float target_motion, float min_size,
+                  float* d_out_field, DetectResult* d_result, DevBuf& scratch, cudaStream_t stream,
+                  uint64_t* launches);
+
+// ---------------------------------------------------------------------------- almeida
+struct AlmeidaScratch {
+    DevBuf state, partial, hyp, inlier_idx, flags;
+};
+
+int launch_almeida(const ofps_mv* d_entries, size_t n, float aspect, float fov_y_deg, int use_ransac,
+                   size_t num_iters, float inlier_angle_deg, size_t ransac_samples, uint64_t seed,
+                   float* d_quat, AlmeidaScratch& scratch, int sm_count, cudaStream_t stream, uint64_t* launches);
+
+}  // namespace ofpsb
+
+struct ofpsb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t l2_bytes = 0, mem_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host->device staging of the batched host entry points
+    cudaStream_t d2h_stream = nullptr;    // device->host return of their results
+    cudaStream_t stream = nullptr;        // current (own or borrowed)
+    uint64_t launches = 0;
+    // options (ofpsb_set_option)
+    int opt_densify_path = 0;
+    int opt_block_match_kernel = 0;
+    int opt_batch_chunk_pairs = 0;
+    // scratch
+    ofpsb::DevBuf d_frames, d_mv, d_cost, d_entries, d_field, d_field2, d_counts, d_misc, d_detect_scratch;
+    ofpsb::PinBuf h_misc;
+    ofpsb::DensifyScratch densify;
+    ofpsb::AlmeidaScratch almeida;
+    std::vector<cudaEvent_t> events;      // pool for the batch pipeline (no timing)
+};

@@ -1,0 +1,93 @@
+"""K5/K6 parity: the CUDA Almeida estimator against the oracle and the reference's own test matrix.
+
+Tolerance (BASELINE north_star): 1e-4 on the unit quaternion, component-wise after sign
+normalisation, against the oracle's f64 evaluation of the same algorithm; the distance of the
+oracle's f32-sequential evaluation is asserted alongside (SURVEY.md §7 "Almeida tolerance")."""
+import math
+
+import numpy as np
+import pytest
+
+from ofps_b200 import synth
+from reftests import build_field, quat_close, reference_cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ref_fields(oracle):
+    return {(rot, k): build_field(oracle, ang) for rot, k, ang in reference_cases()}
+
+
+def test_reference_rotation_matrix_lsq(ctx, oracle, ref_fields):
+    """almeida-estimator/src/lib.rs:359-364 (test_rotation_default): err < 0.1*rot degrees."""
+    for (rot, k), (field, q_truth) in ref_fields.items():
+        q = ctx.almeida(field, 1.0, 90.0, use_ransac=False)
+        err = math.degrees(oracle.quat_angle_to(q_truth, q.astype(np.float64)))
+        assert err < 0.1 * rot or (k == 0 and err < 1e-3), (rot, k, err)
+        q64 = oracle.almeida_lsq_f64(field, 1.0, 90.0)
+        q32 = oracle.almeida_lsq_f32(field, 1.0, 90.0)
+        assert quat_close(q, q64) < TOL, (rot, k, q, q64)
+        assert quat_close(q32, q64) < TOL
+        assert abs(np.linalg.norm(q) - 1) < 1e-5
+
+
+def test_reference_rotation_matrix_ransac(ctx, oracle, ref_fields):
+    """test_rotation_ransac (almeida:366-372): 100 iterations, same tolerance; same seeded RNG as the oracle."""
+    for (rot, k), (field, q_truth) in ref_fields.items():
+        q = ctx.almeida(field, 1.0, 90.0, use_ransac=True, num_iters=100, seed=1234 + k)
+        err = math.degrees(oracle.quat_angle_to(q_truth, q.astype(np.float64)))
+        assert err < 0.1 * rot or (k == 0 and err < 1e-3), (rot, k, err)
+        qo, cnt, it = oracle.almeida_ransac_f32(field, 1.0, 90.0, 100, 0.05, 1000, seed=1234 + k)
+        assert quat_close(q, qo) < TOL, (rot, k, q, qo)
+
+
+@pytest.mark.parametrize("w,h", [(640, 360), (150, 84)])
+def test_dense_field_vs_oracle(ctx, oracle, w, h):
+    field, q_truth = synth.rotation_field(w, h, 16 / 9, 22.275, (0.3, -0.2, 0.1))
+    q = ctx.almeida(field, 16 / 9, 22.275)
+    q64 = oracle.almeida_lsq_f64(field, 16 / 9, 22.275)
+    q32 = oracle.almeida_lsq_f32(field, 16 / 9, 22.275)
+    assert quat_close(q, q64) < TOL
+    assert quat_close(q32, q64) < TOL
+    assert quat_close(q, q_truth) < TOL
+
+
+def test_dense_1080p_recovers_truth(ctx, oracle):
+    """BASELINE config 2: per-pixel 1080p field (2,073,600 entries), fp32, tol 1e-4."""
+    for euler in [(0.3, -0.2, 0.1), (0.0, 0.0, 0.0), (1.0, 0.5, -0.7)]:
+        field, q_truth = synth.rotation_field(1920, 1080, 16 / 9, 22.275, euler)
+        q = ctx.almeida(field, 16 / 9, 22.275)
+        assert quat_close(q, q_truth) < TOL, (euler, q, q_truth)
+    # multi-CTA path == single-CTA path on the same data (both deterministic)
+    sub = field[:16384]
+    a = ctx.almeida(sub, 16 / 9, 22.275)
+    b = ctx.almeida(field[:16385], 16 / 9, 22.275)
+    assert quat_close(a, b) < 1e-5
+    assert np.array_equal(ctx.almeida(field, 16 / 9, 22.275), ctx.almeida(field, 16 / 9, 22.275))
+
+
+def test_degenerate_inputs(ctx, oracle):
+    ident = np.array([1, 0, 0, 0], np.float32)
+    for n in (0, 1, 2):
+        field, _ = synth.rotation_field(8, 8, 1.0, 90.0, (1.0, 0, 0))
+        q = ctx.almeida(field[:n], 1.0, 90.0)
+        qo = oracle.almeida_lsq_f32(field[:n], 1.0, 90.0)
+        assert quat_close(q, qo) < TOL
+    assert quat_close(ctx.almeida(np.zeros((0, 4), np.float32), 1.0, 90.0), ident) == 0
+    # RANSAC with fewer than 3 inliers / entries returns identity (almeida:246-250)
+    assert quat_close(ctx.almeida(field[:2], 1.0, 90.0, use_ransac=True, num_iters=10), ident) == 0
+    assert quat_close(ctx.almeida(np.zeros((0, 4), np.float32), 1.0, 90.0, use_ransac=True, num_iters=10), ident) == 0
+
+
+def test_ransac_rejects_outliers(ctx, oracle):
+    field, q_truth = synth.rotation_field(150, 84, 16 / 9, 22.275, (0.5, 0.3, -0.4))
+    bad = synth.corrupt_field(field, 0.2)
+    q_lsq = ctx.almeida(bad, 16 / 9, 22.275)
+    q_rs = ctx.almeida(bad, 16 / 9, 22.275, use_ransac=True, num_iters=200, seed=7)
+    assert quat_close(q_rs, q_truth) < TOL
+    assert quat_close(q_lsq, q_truth) > quat_close(q_rs, q_truth)
+    qo, cnt, it = oracle.almeida_ransac_f32(bad, 16 / 9, 22.275, 200, 0.05, 1000, seed=7)
+    assert quat_close(q_rs, qo) < TOL
+    assert cnt > 600

@@ -1,0 +1,151 @@
+"""K1/K2 parity: the CUDA block matcher against the oracle's exhaustive search (bit-exact).
+
+The reference has no SAD search; the oracle's orc_block_match IS the
+specification, so these tests pin the kernel to the spec: integer motion vectors and costs
+bit-exact, MotionEntry floats bit-exact (same operation order as av-decoder/src/lib.rs:404-419).
+"""
+import numpy as np
+import pytest
+
+from ofps_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, oracle, prev, cur, block, search, metric):
+    got = ctx.block_match(prev, cur, block, search, metric)
+    mv, cost, ent = oracle.block_match(prev, cur, block, search, metric, threads=oracle.max_threads(), fast=False)
+    assert got["n_blocks"] == (prev.shape[0] // block) * (prev.shape[1] // block)
+    np.testing.assert_array_equal(got["cost"], cost)
+    np.testing.assert_array_equal(got["mv"], mv)
+    assert got["entries"].tobytes() == ent.tobytes()
+    return got
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_c1_640x360_b16_r8(ctx, oracle, metric):
+    """BASELINE config 0: 640x360, 16x16 blocks, +-8 (40x22 full blocks, 8 remainder rows ignored)."""
+    prev, cur, truth = synth.make_pair(640, 360, 8, index=0)
+    got = _check(ctx, oracle, prev, cur, 16, 8, metric)
+    assert got["mv"].shape == (22, 40, 2)
+    # most blocks follow the global pan: block matcher reports d = -(content motion)
+    gx, gy = truth["global"]
+    frac = np.mean((got["mv"][..., 0] == -gx) & (got["mv"][..., 1] == -gy))
+    assert frac > 0.5
+
+
+@pytest.mark.parametrize("block,search,w,h", [
+    (16, 16, 640, 360), (16, 16, 1920, 1080), (8, 32, 512, 288), (8, 16, 320, 200), (8, 8, 328, 200),
+    (16, 32, 400, 300), (16, 8, 1000, 100),
+])
+def test_tuned_instances(ctx, oracle, block, search, w, h):
+    prev, cur, _ = synth.make_pair(w, h, search, index=3)
+    _check(ctx, oracle, prev, cur, block, search, 0)
+
+
+@pytest.mark.parametrize("block,search,w,h,metric", [
+    (4, 3, 64, 48, 0), (12, 5, 200, 120, 1), (32, 7, 256, 160, 0), (16, 0, 128, 64, 0), (64, 2, 256, 128, 1),
+    (16, 63, 300, 200, 0), (20, 9, 333, 127, 0),
+])
+def test_generic_geometries(ctx, oracle, block, search, w, h, metric):
+    prev, cur, _ = synth.make_pair(w, h, max(search, 1), index=5)
+    _check(ctx, oracle, prev, cur, block, search, metric)
+
+
+def test_generic_kernel_equals_tuned(ctx):
+    prev, cur, _ = synth.make_pair(1920, 1080, 16, index=2, noise_lsb=2)
+    a = ctx.block_match(prev, cur, 16, 16, 0)
+    ctx.set_option("block_match_kernel", 1)
+    try:
+        b = ctx.block_match(prev, cur, 16, 16, 0)
+    finally:
+        ctx.set_option("block_match_kernel", 0)
+    for k in ("mv", "cost", "entries"):
+        np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_ties_prefer_short_vectors(ctx, oracle):
+    """Flat frames: every candidate has cost 0 -> the zero vector wins (tie-break on d^2)."""
+    prev = np.full((96, 160), 77, np.uint8)
+    cur = prev.copy()
+    got = _check(ctx, oracle, prev, cur, 16, 16, 0)
+    assert not got["mv"].any() and not got["cost"].any()
+    # periodic texture: many exact matches, the nearest one must win
+    x = (np.arange(160) % 8 * 30).astype(np.uint8)
+    prev = np.tile(x, (96, 1))
+    _check(ctx, oracle, prev, prev.copy(), 16, 16, 0)
+    _check(ctx, oracle, prev, np.roll(prev, 3, axis=1), 8, 16, 0)
+
+
+def test_noise_and_extremes(ctx, oracle):
+    rng = np.random.default_rng(11)
+    prev = rng.integers(0, 256, (144, 208), dtype=np.uint8)
+    cur = rng.integers(0, 256, (144, 208), dtype=np.uint8)
+    _check(ctx, oracle, prev, cur, 16, 16, 0)
+    _check(ctx, oracle, prev, cur, 16, 16, 1)
+    # maximum cost: all-0 vs all-255
+    z = np.zeros((64, 64), np.uint8)
+    f = np.full((64, 64), 255, np.uint8)
+    got = _check(ctx, oracle, z, f, 16, 8, 0)
+    assert (got["cost"] == 16 * 16 * 255).all()
+    got = _check(ctx, oracle, z, f, 16, 8, 1)
+    assert (got["cost"] == 16 * 16 * 255 * 255).all()
+
+
+def test_small_and_empty_frames(ctx, oracle):
+    prev, cur, _ = synth.make_pair(16, 16, 4, index=1, n_rects=0)
+    _check(ctx, oracle, prev, cur, 16, 16, 0)     # a single block, only (0,0) is legal
+    got = ctx.block_match(prev[:8], cur[:8], 16, 16, 0)   # no full block at all
+    assert got["n_blocks"] == 0 and got["mv"].size == 0
+
+
+def test_batch_and_stream_mode(ctx, oracle):
+    from ofps_b200 import capi
+    frames = np.stack([synth.textured_plane(100 + i, 320, 192) for i in range(6)])
+    # independent pairs
+    got = ctx.block_match(frames[:-1], frames[1:], 16, 8, 0)
+    for i in range(5):
+        mv, cost, ent = oracle.block_match(frames[i], frames[i + 1], 16, 8, 0)
+        np.testing.assert_array_equal(got["mv"][i], mv)
+        np.testing.assert_array_equal(got["cost"][i], cost)
+    # stream mode: cur == prev + one frame, each frame uploaded once, small chunks
+    ctx.set_option("batch_chunk_pairs", 2)
+    try:
+        nb = 12 * 20
+        mv = np.empty((5, 12, 20, 2), np.int16)
+        n = ctx.block_match_raw(frames.ctypes.data, frames.ctypes.data + 320 * 192, 320, 192, 320, 320 * 192, 5, 16, 8,
+                                0, mv, None, None)
+        assert n == nb
+        np.testing.assert_array_equal(mv, got["mv"])
+    finally:
+        ctx.set_option("batch_chunk_pairs", 0)
+
+
+def test_strided_rows(ctx, oracle):
+    """Row stride larger than the width (and not a multiple of 4: the unaligned load path)."""
+    import ctypes as C
+    from ofps_b200 import capi
+    prev, cur, _ = synth.make_pair(322, 100, 8, index=9)
+    pad_p = np.zeros((100, 331), np.uint8)
+    pad_c = np.zeros((100, 331), np.uint8)
+    pad_p[:, :322], pad_c[:, :322] = prev, cur
+    mv = np.empty((6, 20, 2), np.int16)
+    cost = np.empty((6, 20), np.uint32)
+    nb = C.c_size_t()
+    capi.check(capi.lib().ofpsb_block_match(ctx._h, pad_p.ctypes.data, pad_c.ctypes.data, 322, 100, 331, 16, 8, 0,
+                                            mv.ctypes.data, cost.ctypes.data, None, C.byref(nb)))
+    omv, ocost, _ = oracle.block_match(prev, cur, 16, 8, 0)
+    np.testing.assert_array_equal(mv, omv)
+    np.testing.assert_array_equal(cost, ocost)
+
+
+def test_invalid_arguments(ctx):
+    from ofps_b200 import capi
+    prev = np.zeros((64, 64), np.uint8)
+    with pytest.raises(capi.OfpsError) as e:
+        ctx.block_match(prev, prev, 16, 64, 0)      # range > 63
+    assert e.value.code == capi.E_INVALID
+    with pytest.raises(capi.OfpsError):
+        ctx.block_match(prev, prev, 6, 4, 0)        # block not a multiple of 4
+    with pytest.raises(capi.OfpsError):
+        ctx.block_match(prev, prev, 16, 4, 7)       # unknown metric
