@@ -130,6 +130,34 @@ def make_batch(n_pairs: int, w: int, h: int, search: int, noise_lsb: int = 0, fi
     return prev, cur
 
 
+def make_stream(n_frames: int, w: int, h: int, search: int, n_rects: int = 8, seed: int = BASE_SEED,
+                first_index: int = 0) -> np.ndarray:
+    """``n_frames`` consecutive luma frames [n, h, w] of one synthetic video: frame i+1 is frame i
+    panned by an integer global motion with ``n_rects`` rectangles moved on their own (the
+    :func:`make_pair` recipe, chained), so pair (i, i+1) is a real motion pair for every i."""
+    rng = _Rng(seed + 7919 * (first_index + 1))
+    frames = np.empty((n_frames, h, w), np.uint8)
+    frames[0] = textured_plane(rng.next(), w, h)
+    half = max(search // 2, 0)
+    for i in range(1, n_frames):
+        prev = frames[i - 1]
+        fill = textured_plane(rng.next(), w, h)
+        gx, gy = rng.randint(-half, half), rng.randint(-half, half)
+        cur = shift_plane(prev, fill, gx, gy)
+        for _ in range(n_rects):
+            rw = rng.randint(min(64, w // 2), min(256, w // 2))
+            rh = rng.randint(min(64, h // 2), min(256, h // 2))
+            x0 = rng.randint(0, w - rw)
+            y0 = rng.randint(0, h - rh)
+            dx, dy = rng.randint(-search, search), rng.randint(-search, search)
+            cx0, cx1 = max(x0, dx), min(x0 + rw, w + dx)
+            cy0, cy1 = max(y0, dy), min(y0 + rh, h + dy)
+            if cx1 > cx0 and cy1 > cy0:
+                cur[cy0:cy1, cx0:cx1] = prev[cy0 - dy:cy1 - dy, cx0 - dx:cx1 - dx]
+        frames[i] = cur
+    return frames
+
+
 # ----------------------------------------------------------------------------- estimator fields
 def _quat_from_euler(roll: float, pitch: float, yaw: float) -> np.ndarray:
     sr, cr = math.sin(roll * 0.5), math.cos(roll * 0.5)
