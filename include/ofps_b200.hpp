@@ -1,0 +1,264 @@
+// ofps_b200.hpp — C++17 host-side mirror of the reference's plugin interface for the hot path,
+// layered over the C ABI (ofps_b200.h).  Header-only; link with -lofps_b200.
+//
+// The reference is Rust; its plugin traits are not FFI-safe, so a drop-in needs a
+// thin Rust cdylib per plugin (sources under rust/, binding shown in INTEGRATION.md).  This header
+// is the same surface for C++ hosts, with the reference's names, argument meaning, property names /
+// bounds and error behaviour:
+//
+//   ofps::Decoder::process_frame / get_framerate / get_aspect      ofps/src/decoder.rs:45-73
+//   ofps::Detector::detect_motion                                   ofps/src/detection.rs:6-12
+//   ofps::Estimator::estimate / motion_step                         ofps/src/estimator.rs:8-54
+//   ofps::Properties::props_mut                                     ofps/src/plugins/properties.rs:6-18
+//   ofps::MotionField, MotionFieldDensifier (read side)             ofps/src/motion_field.rs:7-115
+//   ofps::StandardCamera::new / aspect_ratio / fov                  ofps/src/camera.rs:26-35, 166-177
+#ifndef OFPS_B200_HPP
+#define OFPS_B200_HPP
+
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <variant>
+#include <vector>
+
+#include "ofps_b200.h"
+
+namespace ofps_b200 {
+
+// anyhow::Error of the reference's Decoder / Estimator results
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+inline void check(int rc)
+{
+    if (rc != OFPSB_OK) throw Error(rc, ofpsb_last_error());
+}
+
+using MotionEntry = ofps_mv;                       // (Point2 pos, Vector2 motion), ofps/src/decoder.rs:40
+using MotionVectors = std::vector<MotionEntry>;    // ofps/src/decoder.rs:42
+struct RGBA { uint8_t r, g, b, a; };               // ofps/src/decoder.rs:12-26
+
+// One context (device, stream, scratch) shared by the plugins of a host thread.  Send, not Sync.
+class Context {
+public:
+    explicit Context(int device = 0) { check(ofpsb_create(device, &ctx_)); }
+    ~Context() { ofpsb_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    ofpsb_ctx* get() const { return ctx_; }
+
+private:
+    ofpsb_ctx* ctx_ = nullptr;
+};
+
+// ---- Properties (ofps/src/plugins/properties.rs:6-18, 120-125)
+struct FloatProp { float* val; float min, max; };
+struct UsizeProp { size_t* val; size_t min, max; };
+struct BoolProp { bool* val; };
+using PropertyMut = std::variant<FloatProp, UsizeProp, BoolProp>;
+using PropList = std::vector<std::pair<const char*, PropertyMut>>;
+
+// ---- MotionField (ofps/src/motion_field.rs:7-115): cell-major [x0,y0,x1,y1,...], cell = y*w + x
+class MotionField {
+public:
+    MotionField(size_t width, size_t height) : vf_(2 * width * height, 0.0f), width_(width) {}
+    std::pair<size_t, size_t> dim() const { return {width_, width_ ? vf_.size() / 2 / width_ : 0}; }
+    size_t size() const { return vf_.size() / 2; }
+    const float* as_slice() const { return vf_.data(); }
+    float* as_mut_slice() { return vf_.data(); }
+    std::array<float, 2> get_motion(size_t x, size_t y) const
+    {
+        const size_t i = y * width_ + x;
+        return {vf_[2 * i], vf_[2 * i + 1]};
+    }
+    void set_motion(size_t x, size_t y, std::array<float, 2> m)
+    {
+        const size_t i = y * width_ + x;
+        vf_[2 * i] = m[0];
+        vf_[2 * i + 1] = m[1];
+    }
+    // motion_iter(): positions are cell corners (x/w, y/h), motion_field.rs:104-112
+    MotionVectors motion_iter() const
+    {
+        MotionVectors out;
+        const auto [w, h] = dim();
+        for (size_t y = 0; y < h; y++)
+            for (size_t x = 0; x < w; x++) {
+                const auto m = get_motion(x, y);
+                out.push_back({(float)x / (float)w, (float)y / (float)h, m[0], m[1]});
+            }
+        return out;
+    }
+
+private:
+    std::vector<float> vf_;
+    size_t width_;
+};
+
+// MotionFieldDensifier::add_vector over a slice + MotionField::from (motion_field.rs:133-190, 297-308)
+inline MotionField densify(Context& ctx, const MotionEntry* entries, size_t n, size_t width, size_t height)
+{
+    MotionField mf(width, height);
+    check(ofpsb_densify(ctx.get(), entries, n, width, height, mf.as_mut_slice(), nullptr));
+    return mf;
+}
+
+// ---- StandardCamera (ofps/src/camera.rs:9-35): only what the estimator boundary needs
+class StandardCamera {
+public:
+    StandardCamera(float aspect_ratio, float fov_y_deg) : aspect_(aspect_ratio), fov_y_(fov_y_deg) {}
+    float aspect_ratio() const { return aspect_; }
+    // (horizontal, vertical) field of view in degrees (camera.rs:166-177)
+    std::pair<float, float> fov() const
+    {
+        const float half = std::tan(fov_y_ * 0.017453292519943295f / 2.0f);
+        return {std::atan(half * aspect_) * 2.0f / 0.017453292519943295f, fov_y_};
+    }
+
+private:
+    float aspect_, fov_y_;
+};
+
+// ---- Detector: block-motion-detector/src/lib.rs:13-119
+class BlockMotionDetection {
+public:
+    float min_size = 0.05f;
+    size_t subdivide = 3;
+    float target_motion = 0.003f;
+
+    explicit BlockMotionDetection(std::shared_ptr<Context> ctx) : ctx_(std::move(ctx)) {}
+
+    PropList props_mut()
+    {
+        return {{"Min size", FloatProp{&min_size, 0.01f, 1.0f}},
+                {"Subdivisions", UsizeProp{&subdivide, 1, 16}},
+                {"Target motion", FloatProp{&target_motion, 0.0001f, 0.1f}}};
+    }
+
+    // None = no motion.  The detector has no error channel in the reference; a device failure throws.
+    std::optional<std::pair<size_t, MotionField>> detect_motion(const MotionEntry* motion, size_t n) const
+    {
+        size_t dim = 0;
+        check(ofpsb_block_dim(min_size, subdivide, &dim));
+        MotionField mf(dim, dim);
+        int has = 0;
+        size_t area = 0;
+        check(ofpsb_detect_block_motion(ctx_->get(), motion, n, min_size, subdivide, target_motion, &has, &area, &dim,
+                                        mf.as_mut_slice(), mf.size()));
+        if (!has) return std::nullopt;
+        return std::make_pair(area, std::move(mf));
+    }
+    std::optional<std::pair<size_t, MotionField>> detect_motion(const MotionVectors& motion) const
+    {
+        return detect_motion(motion.data(), motion.size());
+    }
+
+private:
+    std::shared_ptr<Context> ctx_;
+};
+
+// ---- Estimator: almeida-estimator/src/lib.rs:57-121
+struct Pose {
+    std::array<float, 4> rotation;      // UnitQuaternion (w, i, j, k)
+    std::array<float, 3> translation;   // always zero (almeida:120)
+};
+
+class AlmeidaEstimator {
+public:
+    bool use_ransac = true;
+    size_t num_iters = 200;
+    float inlier_angle = 0.05f;
+    size_t ransac_samples = 1000;
+    uint64_t seed = 0;   // the reference draws from thread_rng(); here the draw is seeded and advances per call
+
+    explicit AlmeidaEstimator(std::shared_ptr<Context> ctx) : ctx_(std::move(ctx)) {}
+
+    PropList props_mut()
+    {
+        return {{"Use ransac", BoolProp{&use_ransac}},
+                {"Ransac iters", UsizeProp{&num_iters, 1, 500}},
+                {"Inlier threshold", FloatProp{&inlier_angle, 0.01f, 1.0f}},
+                {"Ransac samples", UsizeProp{&ransac_samples, 100, 16000}}};
+    }
+
+    // `move_magnitude` is ignored, as in the reference (almeida:105)
+    Pose estimate(const MotionEntry* motion, size_t n, const StandardCamera& camera, std::optional<float> = std::nullopt)
+    {
+        Pose p{{1, 0, 0, 0}, {0, 0, 0}};
+        check(ofpsb_almeida(ctx_->get(), motion, n, camera.aspect_ratio(), camera.fov().second, use_ransac ? 1 : 0,
+                            num_iters, inlier_angle, ransac_samples, seed++, p.rotation.data()));
+        return p;
+    }
+
+private:
+    std::shared_ptr<Context> ctx_;
+};
+
+// ---- Decoder: a luma frame source + the block matcher, emitting what av-decoder emits
+// (av-decoder/src/lib.rs:396-419): one MotionEntry per block, appended to the caller's vector.
+class BlockMatchDecoder {
+public:
+    int block = 16, range = 16, metric = OFPSB_METRIC_SAD;
+    bool emit_zero_motion = true;   // FFmpeg exports nothing for skipped blocks; default keeps every block
+
+    // `next_frame(luma)` fills a width*height u8 luma plane and returns false at end of stream.
+    template <typename F>
+    BlockMatchDecoder(std::shared_ptr<Context> ctx, int width, int height, double framerate, F next_frame)
+        : ctx_(std::move(ctx)), w_(width), h_(height), fps_(framerate), next_(std::move(next_frame)),
+          prev_((size_t)width * height), cur_((size_t)width * height)
+    {
+    }
+
+    PropList props_mut() { return {}; }
+    std::optional<double> get_framerate() const { return fps_ > 0 ? std::optional<double>(fps_) : std::nullopt; }
+    std::optional<std::pair<size_t, size_t>> get_aspect() const { return std::make_pair((size_t)w_, (size_t)h_); }
+
+    // Ok(true): vectors appended; Ok(false): frame had none (first frame); throws Error at end of stream /
+    // on failure.  `out_frame` (RGBA, cleared then filled) and `skip_frames` as in decoder.rs:54-59.
+    bool process_frame(MotionVectors& field, std::vector<RGBA>* out_frame, size_t* out_height, size_t skip_frames)
+    {
+        for (size_t i = 0; i <= skip_frames; i++) {
+            prev_.swap(cur_);
+            if (!next_(cur_.data())) throw Error(OFPSB_E_IO, "end of stream");
+            have_ = have_ < 2 ? have_ + 1 : 2;
+        }
+        if (out_frame) {
+            out_frame->clear();
+            for (uint8_t v : cur_) out_frame->push_back({v, v, v, 255});
+            if (out_height) *out_height = (size_t)h_;
+        }
+        if (have_ < 2) return false;
+        size_t nb = 0;
+        scratch_.resize((size_t)(w_ / block) * (h_ / block));
+        check(ofpsb_block_match(ctx_->get(), prev_.data(), cur_.data(), w_, h_, w_, block, range, metric, nullptr, nullptr,
+                                scratch_.data(), &nb));
+        size_t pushed = 0;
+        for (size_t i = 0; i < nb; i++)
+            if (emit_zero_motion || scratch_[i].mx != 0.0f || scratch_[i].my != 0.0f) {
+                field.push_back(scratch_[i]);
+                pushed++;
+            }
+        return pushed > 0;
+    }
+
+private:
+    std::shared_ptr<Context> ctx_;
+    int w_, h_;
+    double fps_;
+    std::function<bool(uint8_t*)> next_;
+    std::vector<uint8_t> prev_, cur_;
+    MotionVectors scratch_;
+    int have_ = 0;
+};
+
+}  // namespace ofps_b200
+
+#endif  // OFPS_B200_HPP

@@ -1,0 +1,77 @@
+//! Raw bindings of `include/ofps_b200.h` (hand-written; the header is small and stable).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct ofps_mv {
+    pub px: f32,
+    pub py: f32,
+    pub mx: f32,
+    pub my: f32,
+}
+
+#[repr(C)]
+pub struct ofpsb_ctx {
+    _private: [u8; 0],
+}
+
+pub const OFPSB_OK: c_int = 0;
+pub const OFPSB_METRIC_SAD: c_int = 0;
+pub const OFPSB_METRIC_SSD: c_int = 1;
+
+extern "C" {
+    pub fn ofpsb_create(device: c_int, out: *mut *mut ofpsb_ctx) -> c_int;
+    pub fn ofpsb_destroy(ctx: *mut ofpsb_ctx);
+    pub fn ofpsb_last_error() -> *const c_char;
+    pub fn ofpsb_block_match(
+        ctx: *mut ofpsb_ctx, prev: *const u8, cur: *const u8, w: c_int, h: c_int, stride: c_int, block: c_int,
+        range: c_int, metric: c_int, mv_xy: *mut i16, cost: *mut u32, entries: *mut ofps_mv, n_blocks: *mut usize,
+    ) -> c_int;
+    pub fn ofpsb_block_dim(min_size: f32, subdivide: usize, dim: *mut usize) -> c_int;
+    pub fn ofpsb_detect_block_motion(
+        ctx: *mut ofpsb_ctx, entries: *const ofps_mv, n: usize, min_size: f32, subdivide: usize, target_motion: f32,
+        has_motion: *mut c_int, area: *mut usize, dim: *mut usize, field_xy: *mut f32, field_cap_cells: usize,
+    ) -> c_int;
+    pub fn ofpsb_densify(
+        ctx: *mut ofpsb_ctx, entries: *const ofps_mv, n: usize, gw: usize, gh: usize, field_xy: *mut f32,
+        counts: *mut f32,
+    ) -> c_int;
+    pub fn ofpsb_almeida(
+        ctx: *mut ofpsb_ctx, entries: *const ofps_mv, n: usize, aspect: f32, fov_y_deg: f32, use_ransac: c_int,
+        num_iters: usize, inlier_angle_deg: f32, ransac_samples: usize, seed: u64, quat_wijk: *mut f32,
+    ) -> c_int;
+    pub fn ofpsb_set_stream(ctx: *mut ofpsb_ctx, stream: *mut c_void) -> c_int;
+}
+
+/// Owning handle.  `Send` (the reference requires plugins to be `Send`), not `Sync`: the library allows a
+/// context to move between threads but not to be used concurrently.
+pub struct Context(pub *mut ofpsb_ctx);
+unsafe impl Send for Context {}
+
+impl Context {
+    pub fn new(device: i32) -> Result<Self, String> {
+        let mut p = std::ptr::null_mut();
+        let rc = unsafe { ofpsb_create(device, &mut p) };
+        if rc != OFPSB_OK {
+            return Err(last_error());
+        }
+        Ok(Self(p))
+    }
+}
+
+impl Drop for Context {
+    fn drop(&mut self) {
+        unsafe { ofpsb_destroy(self.0) }
+    }
+}
+
+pub fn last_error() -> String {
+    unsafe { std::ffi::CStr::from_ptr(ofpsb_last_error()).to_string_lossy().into_owned() }
+}
+
+/// `MotionEntry` is a Rust tuple `(Point2<f32>, Vector2<f32>)` whose field order is not ABI-guaranteed:
+/// copy into the C layout instead of transmuting.
+pub fn to_c(motion: &[((f32, f32), (f32, f32))]) -> Vec<ofps_mv> {
+    motion.iter().map(|&((px, py), (mx, my))| ofps_mv { px, py, mx, my }).collect()
+}
