@@ -75,7 +75,9 @@ uint64_t ofpsb_launch_count(ofpsb_ctx *ctx);
 void *ofpsb_get_stream(ofpsb_ctx *ctx);
 /* Tuning / test knobs; unknown keys return OFPSB_E_INVALID.
  *   "densify_path"        0 = by size (default), 1 = force the scan path, 2 = force the sort path
- *   "block_match_kernel"  0 = tuned instance when one exists (default), 1 = force the generic kernel
+ *   "block_match_kernel"  0 = best instance (TMA-staged, else LDG-staged, else generic; default),
+ *                         1 = force the generic kernel, 2 = force the LDG-staged tile kernel,
+ *                         3 = TMA-staged, alternative tile shape
  *   "batch_chunk_pairs"   pairs per pipelined chunk in ofpsb_block_match_batch (0 = automatic) */
 int ofpsb_set_option(ofpsb_ctx *ctx, const char *key, long long value);
 

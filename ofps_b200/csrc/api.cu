@@ -146,8 +146,13 @@ int launch_bm(ofpsb_ctx* ctx, const BlockMatchParams& p)
         if (p.mv_xy) q.mv_xy = p.mv_xy + 2 * nb * first;
         if (p.cost) q.cost = p.cost + nb * first;
         if (p.entries) q.entries = p.entries + nb * first;
-        int rc = ctx->opt_block_match_kernel == 1 ? launch_block_match_generic(q, ctx->stream, &ctx->launches)
-                                                  : launch_block_match(q, ctx->stream, &ctx->launches);
+        int rc;
+        switch (ctx->opt_block_match_kernel) {
+            case 1: rc = launch_block_match_generic(q, ctx->stream, &ctx->launches); break;
+            case 2: rc = launch_block_match_ldg(q, ctx->stream, &ctx->launches); break;
+            case 3: rc = launch_block_match(q, ctx->stream, &ctx->launches, 1); break;
+            default: rc = launch_block_match(q, ctx->stream, &ctx->launches, 0); break;
+        }
         if (rc) return rc;
     }
     return OFPSB_OK;
@@ -328,7 +333,7 @@ int ofpsb_set_option(ofpsb_ctx* ctx, const char* key, long long value)
         return OFPSB_E_INVALID;
     }
     if (!strcmp(key, "densify_path") && value >= 0 && value <= 2) ctx->opt_densify_path = (int)value;
-    else if (!strcmp(key, "block_match_kernel") && value >= 0 && value <= 1) ctx->opt_block_match_kernel = (int)value;
+    else if (!strcmp(key, "block_match_kernel") && value >= 0 && value <= 3) ctx->opt_block_match_kernel = (int)value;
     else if (!strcmp(key, "batch_chunk_pairs") && value >= 0 && value <= 65535) ctx->opt_batch_chunk_pairs = (int)value;
     else {
         set_error("set_option: unknown key or value out of range: %s = %lld", key, value);

@@ -1,0 +1,314 @@
+// K1+K2, TMA-staged variant: exhaustive block matching where the frame tiles are moved from
+// HBM/L2 into shared memory by the Tensor Memory Accelerator instead of by SM instructions.
+//
+// Why: on B200 `VABSDIFF4.U8.ACC` issues at 64 lanes/clk/SM on the ALU pipe (measured,
+// profiles/r1_microbench_int_pipes.txt) and an exhaustive SAD search is bound by exactly that pipe.
+// In the first tile kernel (block_match.cu) 57 % of the executed instructions were NOT the SAD
+// instruction: window staging with bounds checks, the funnel-shift pass that builds the four
+// byte-shifted window copies, 64-bit key packing (profiles/r1_block_match_v1_ncu.md).  Here
+//   * the search window and the current tile are two TMA box loads (u8 tensor maps; out-of-frame
+//     bytes are zero-filled by the TMA unit, so there is no bounds logic at all).  The three
+//     byte-shifted window copies are then derived in shared memory with one funnel shift per word
+//     (measured on B200: a TMA box must start on a 16-byte boundary of the innermost dimension —
+//     a u8 box at x+1 raises "illegal instruction", tools/tma_test.cu — so the TMA unit cannot
+//     produce the shifted copies itself);
+//   * work items are ordered (dy group, shift class, block, dx/4) so that the lanes of a warp read
+//     consecutive words of ONE copy: conflict-free without padding the TMA destination;
+//   * each thread folds its G candidates into a 32-bit key `cost<<7 | rank(dy)` (one IMAD on the
+//     FMA pipe + one VIMNMX per candidate), and the per-block argmin is finished by one warp per
+//     block with two REDUX.MIN passes over shared memory.
+// The result is bit-identical to the generic kernel and the oracle (same tie-break:
+// lexicographic (cost, dx^2+dy^2, dy, dx)).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "block_match_common.cuh"
+
+namespace ofpsb {
+
+namespace {
+
+using namespace bm;
+
+template <int B, int R, int G, int TBX, int NT>
+struct TmaCfg {
+    static constexpr int ND = 2 * R + 1;
+    static constexpr int NG = (ND + G - 1) / G;
+    static constexpr int RA = (R + 15) & ~15;                     // window origin on a 16-byte boundary (TMA)
+    static constexpr int XPAD = RA - R;
+    static constexpr int WCOLS = B / 4;
+    static constexpr int WIN_W = TBX * B + 2 * RA;                // bytes per window row (TMA box inner dim)
+    static constexpr int ROW_WORDS = WIN_W / 4;
+    static constexpr int WIN_H_VALID = B + 2 * R;                 // rows the TMA box carries
+    static constexpr int WIN_H = B + NG * G - 1;                  // rows addressed (incl. masked dy padding)
+    static constexpr int COPY_BYTES = (WIN_H * WIN_W + 127) & ~127;
+    static constexpr int COPY_WORDS = COPY_BYTES / 4;
+    static constexpr int CUR_W = TBX * B;                         // bytes per current-tile row
+    static constexpr int CUR_BYTES = (B * CUR_W + 127) & ~127;
+    static constexpr int CUR_ROW_WORDS = CUR_W / 4;
+    static constexpr int FIRST0 = (0 - XPAD) & 3, FIRST1 = (1 - XPAD) & 3, FIRST2 = (2 - XPAD) & 3, FIRST3 = (3 - XPAD) & 3;
+    static constexpr int nq(int first) { return first < ND ? (ND - first + 3) / 4 : 0; }
+    static constexpr int NQ0 = nq(FIRST0), NQ1 = nq(FIRST1), NQ2 = nq(FIRST2), NQ3 = nq(FIRST3);
+    static constexpr int ITEMS_G = TBX * ND;
+    static constexpr int ITEMS = NG * ITEMS_G;
+    static constexpr int ROUNDS = (ITEMS + NT - 1) / NT;
+    static constexpr int SLOTS = TBX * NG * ND;                   // per-item results, block-major
+    static constexpr uint32_t TX_BYTES = (uint32_t)WIN_W * WIN_H_VALID + (uint32_t)B * CUR_W;
+    static constexpr size_t SMEM_BYTES = 4 * (size_t)COPY_BYTES + CUR_BYTES + (size_t)SLOTS * 8 + 16;
+    static_assert(B % 4 == 0 && B >= 4 && B <= 16, "TMA instances cover blocks up to 16x16 (32-bit keys)");
+    static_assert(CUR_W % 16 == 0 && WIN_W % 16 == 0 && WIN_W <= 256 && WIN_H_VALID <= 256 && CUR_W <= 256, "TMA box limits");
+    static_assert(NQ0 + NQ1 + NQ2 + NQ3 == ND, "shift classes must cover every dx");
+    static_assert(ND <= 127 && 2 * (NG * G - R) < 128, "key fields: 7-bit dy rank, 7-bit dx/dy indices");
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+
+// cost * 128 + rank on the FMA pipe (IMAD): the ALU pipe is the one the SAD instruction saturates
+__device__ __forceinline__ uint32_t fold_key(uint32_t cost, uint32_t rank)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(r) : "r"(cost), "r"(rank));
+    return r;
+}
+
+template <int B, int R, int G, int TBX, int NT, int METRIC>
+__global__ void __launch_bounds__(NT) block_match_tma_kernel(const __grid_constant__ CUtensorMap map_prev,
+                                                             const __grid_constant__ CUtensorMap map_cur,
+                                                             const BlockMatchParams p)
+{
+    using C = TmaCfg<B, R, G, TBX, NT>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint32_t* win = reinterpret_cast<uint32_t*>(smem_raw);                         // [4][WIN_H][ROW_WORDS]
+    uint32_t* curs = reinterpret_cast<uint32_t*>(smem_raw + 4 * C::COPY_BYTES);    // [B][CUR_ROW_WORDS]
+    uint32_t* r_cost = reinterpret_cast<uint32_t*>(smem_raw + 4 * C::COPY_BYTES + C::CUR_BYTES);   // [SLOTS]
+    uint32_t* r_pos = r_cost + C::SLOTS;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(r_pos + C::SLOTS);
+
+    const int tid = threadIdx.x;
+    const int tile_bx0 = blockIdx.x * TBX;
+    const int by = blockIdx.y;
+    const int pair = blockIdx.z;
+    const int x0 = tile_bx0 * B;
+    const int y0 = by * B;
+
+    if (tid == 0) {
+        const uint32_t b32 = smem_u32(bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b32));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(C::TX_BYTES) : "memory");
+        const int wx = x0 - C::RA, wy = y0 - R + p.halo_top;   // tensor row 0 = first halo row
+        tma_load_3d(smem_u32(win), &map_prev, wx, wy, pair, b32);
+        tma_load_3d(smem_u32(curs), &map_cur, x0, y0, pair, b32);
+    }
+    // masked results for slots no item writes (none today, cheap insurance for partial rounds)
+    for (int i = tid; i < C::SLOTS; i += NT) r_cost[i] = 0xFFFFFFFFu;
+    __syncthreads();   // barrier init visible to the waiters
+    {
+        const uint32_t b32 = smem_u32(bar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                : "=r"(done)
+                : "r"(b32), "r"(0u)
+                : "memory");
+        }
+    }
+
+    // byte-shifted copies 1..3: copy_s[row][k] = bytes [4k+s, 4k+s+4) of the window row
+    for (int idx = tid; idx < C::WIN_H_VALID * C::ROW_WORDS; idx += NT) {
+        const int k = idx % C::ROW_WORDS;
+        const uint32_t lo = win[idx];
+        const uint32_t hi = (k + 1 < C::ROW_WORDS) ? win[idx + 1] : 0u;
+        win[C::COPY_WORDS + idx] = __funnelshift_r(lo, hi, 8);
+        win[2 * C::COPY_WORDS + idx] = __funnelshift_r(lo, hi, 16);
+        win[3 * C::COPY_WORDS + idx] = __funnelshift_r(lo, hi, 24);
+    }
+    __syncthreads();
+
+    // candidate rows valid for the whole CTA (depends on by only)
+    const int dy_lo = max(-R, -p.halo_top - y0);                              // y0 + dy >= -halo_top
+    const int dy_hi = min(R, p.strip_h + p.halo_bottom - B - y0);             // y0 + dy + B <= strip_h + halo_bottom
+    const bool all_dy = dy_lo == -R && dy_hi == R;
+
+#pragma unroll 1
+    for (int round = 0; round < C::ROUNDS; round++) {
+        const int item = round * NT + tid;
+        if (item >= C::ITEMS) break;
+        const int g = item / C::ITEMS_G;
+        int t = item - g * C::ITEMS_G;
+        int s, b, q;
+        if (t < TBX * C::NQ0) { s = 0; b = t / C::NQ0; q = t - b * C::NQ0; }
+        else if ((t -= TBX * C::NQ0) < TBX * C::NQ1) { s = 1; b = t / C::NQ1; q = t - b * C::NQ1; }
+        else if ((t -= TBX * C::NQ1) < TBX * C::NQ2) { s = 2; b = t / C::NQ2; q = t - b * C::NQ2; }
+        else { t -= TBX * C::NQ2; s = 3; b = t / (C::NQ3 > 0 ? C::NQ3 : 1); q = t - b * C::NQ3; }
+        const int dxi = 4 * q + ((s - C::XPAD) & 3);
+        const int xoff = b * B + dxi + C::XPAD;          // xoff & 3 == s
+        const int dyi0 = g * G;
+
+        uint32_t acc[G];
+#pragma unroll
+        for (int i = 0; i < G; i++) acc[i] = 0;
+        const uint32_t* wbase = win + s * C::COPY_WORDS + (xoff >> 2) + dyi0 * C::ROW_WORDS;
+        const uint32_t* cbase = curs + b * C::WCOLS;
+#pragma unroll 1
+        for (int c = 0; c < C::WCOLS; c++) {
+            uint32_t cw[B];
+#pragma unroll
+            for (int r = 0; r < B; r++) cw[r] = cbase[r * C::CUR_ROW_WORDS + c];
+            const uint32_t* wp = wbase + c;
+#pragma unroll
+            for (int rr = 0; rr < B + G - 1; rr++) {
+                const uint32_t pw = wp[rr * C::ROW_WORDS];
+#pragma unroll
+                for (int gi = 0; gi < G; gi++) {
+                    const int r = rr - gi;
+                    if (r >= 0 && r < B) acc[gi] = cost4<METRIC>(cw[r], pw, acc[gi]);
+                }
+            }
+        }
+
+        // fold the G candidates of this (block, dx): key = cost<<7 | rank(dy), rank orders (|dy|, dy).
+        // The dy group index is made a compile-time constant so that every rank is an immediate, and
+        // interior tile rows (every dy legal: CTA-uniform) skip the per-candidate range test.
+        const int bx = tile_bx0 + b;
+        const int dx = dxi - R;
+        const int px = bx * B + dx;
+        const bool x_ok = bx < p.nbx && px >= 0 && px + B <= p.w;
+        uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+        for (int gg = 0; gg < C::NG; gg++) {
+            if (g != gg) continue;
+            if (all_dy) {
+#pragma unroll
+                for (int gi = 0; gi < G; gi++) {
+                    const int dy = gg * G + gi - R;
+                    if (dy <= R) best = min(best, fold_key(acc[gi], (uint32_t)(2 * (dy < 0 ? -dy : dy) - (dy < 0 ? 1 : 0))));
+                }
+            } else {
+#pragma unroll
+                for (int gi = 0; gi < G; gi++) {
+                    const int dy = gg * G + gi - R;
+                    const uint32_t key = fold_key(acc[gi], (uint32_t)(2 * (dy < 0 ? -dy : dy) - (dy < 0 ? 1 : 0)));
+                    if (dy >= dy_lo && dy <= dy_hi) best = min(best, key);
+                }
+            }
+        }
+        uint32_t cost = 0xFFFFFFFFu, pos = 0;
+        if (x_ok && best != 0xFFFFFFFFu) {
+            const int code = (int)(best & 127u);
+            const int ady = (code + 1) >> 1;
+            const int dy = (code & 1) ? -ady : ady;
+            cost = best >> 7;
+            pos = ((uint32_t)(dx * dx + dy * dy) << 14) | ((uint32_t)(dy + R) << 7) | (uint32_t)(dx + R);
+        }
+        const int slot = (b * C::NG + g) * C::ND + dxi;
+        r_cost[slot] = cost;
+        r_pos[slot] = pos;
+    }
+    __syncthreads();
+
+    // one warp per block: min cost, then min position code among the candidates with that cost
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int blk = warp; blk < TBX; blk += NT / 32) {
+        const int bx = tile_bx0 + blk;
+        const uint32_t* rc = r_cost + blk * C::NG * C::ND;
+        const uint32_t* rp = r_pos + blk * C::NG * C::ND;
+        uint32_t cmin = 0xFFFFFFFFu;
+        for (int i = lane; i < C::NG * C::ND; i += 32) cmin = min(cmin, rc[i]);
+        cmin = __reduce_min_sync(0xffffffffu, cmin);
+        uint32_t pmin = 0xFFFFFFFFu;
+        for (int i = lane; i < C::NG * C::ND; i += 32)
+            if (rc[i] == cmin) pmin = min(pmin, rp[i]);
+        pmin = __reduce_min_sync(0xffffffffu, pmin);
+        if (lane == 0 && bx < p.nbx) {
+            const size_t out_idx = (size_t)pair * p.nbx * p.nby + (size_t)by * p.nbx + bx;
+            write_block_outputs(p, out_idx, ((unsigned long long)cmin << 27) | pmin, bx, by);
+        }
+    }
+}
+
+PFN_cuTensorMapEncodeTiled get_encode()
+{
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(ptr);
+    }
+    return fn;
+}
+
+// u8 tensor (x: w valid bytes of each `stride`-byte row, y: rows, z: pairs)
+bool make_map(CUtensorMap* map, const uint8_t* base, int w, int rows, long long stride, long long pair_stride, int pairs,
+              int box_w, int box_h)
+{
+    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    if (!enc) return false;
+    if (pairs <= 1 || pair_stride <= 0) pair_stride = ((stride * (long long)rows) + 15) & ~15ll;
+    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)rows, (cuuint64_t)(pairs > 0 ? pairs : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)stride, (cuuint64_t)pair_stride};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int B, int R, int G, int TBX, int NT>
+int launch_tma(const BlockMatchParams& p, cudaStream_t stream)
+{
+    using C = TmaCfg<B, R, G, TBX, NT>;
+    const int rows_prev = p.halo_top + p.strip_h + p.halo_bottom;
+    const uint8_t* prev_base = p.prev - (long long)p.halo_top * p.stride;
+    CUtensorMap mp, mc;
+    if (!make_map(&mp, prev_base, p.w, rows_prev, p.stride, p.pair_stride, p.n_pairs, C::WIN_W, C::WIN_H_VALID) ||
+        !make_map(&mc, p.cur, p.w, p.strip_h, p.stride, p.pair_stride, p.n_pairs, C::CUR_W, B))
+        return 1;   // not expressible as a tensor map: the caller falls back to the LDG-staged kernel
+    dim3 grid((p.nbx + TBX - 1) / TBX, p.nby, p.n_pairs);
+    if (p.metric == OFPSB_METRIC_SAD) {
+        auto k = block_match_tma_kernel<B, R, G, TBX, NT, OFPSB_METRIC_SAD>;
+        OFPSB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        k<<<grid, NT, C::SMEM_BYTES, stream>>>(mp, mc, p);
+    } else {
+        auto k = block_match_tma_kernel<B, R, G, TBX, NT, OFPSB_METRIC_SSD>;
+        OFPSB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        k<<<grid, NT, C::SMEM_BYTES, stream>>>(mp, mc, p);
+    }
+    OFPSB_CUDA_TRY(cudaGetLastError());
+    return OFPSB_OK;
+}
+
+}  // namespace
+
+// Returns OFPSB_OK when launched, 1 when there is no TMA instance for this geometry / the frame
+// layout cannot be described by a tensor map (16-byte aligned base and strides), <0 on error.
+int launch_block_match_tma(const BlockMatchParams& p, cudaStream_t stream, int variant)
+{
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p.prev) | reinterpret_cast<uintptr_t>(p.cur) | (uintptr_t)p.stride |
+                           (uintptr_t)(p.n_pairs > 1 ? p.pair_stride : 0)) & 15) == 0;
+    if (!aligned || p.w > (1 << 30) || p.stride >= (1ll << 32)) return 1;
+    //                                                       B   R   G  TBX  NT
+    if (p.block == 16 && p.range == 16) return variant == 1 ? launch_tma<16, 16, 17, 8, 544>(p, stream)
+                                                            : launch_tma<16, 16, 17, 4, 288>(p, stream);
+    if (p.block == 16 && p.range == 8) return launch_tma<16, 8, 17, 12, 224>(p, stream);
+    if (p.block == 16 && p.range == 32) return launch_tma<16, 32, 13, 4, 672>(p, stream);
+    if (p.block == 8 && p.range == 32) return launch_tma<8, 32, 22, 8, 544>(p, stream);
+    if (p.block == 8 && p.range == 16) return launch_tma<8, 16, 17, 16, 544>(p, stream);
+    if (p.block == 8 && p.range == 8) return launch_tma<8, 8, 17, 16, 288>(p, stream);
+    return 1;
+}
+
+}  // namespace ofpsb

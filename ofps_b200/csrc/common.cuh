@@ -62,7 +62,12 @@ struct BlockMatchParams {
 
 // Launches the block matcher (tuned template instance if one exists for (block, range),
 // otherwise the generic kernel).  Returns 0 or OFPSB_E_*; *launches += kernels launched.
-int launch_block_match(const BlockMatchParams& p, cudaStream_t stream, uint64_t* launches);
+int launch_block_match(const BlockMatchParams& p, cudaStream_t stream, uint64_t* launches, int variant = 0);
+// TMA-staged instances (block_match_tma.cu).  Returns 0 when launched, 1 when no instance applies
+// (geometry, or base / strides not 16-byte aligned), < 0 on error.
+int launch_block_match_tma(const BlockMatchParams& p, cudaStream_t stream, int variant);
+// LDG-staged tile instances only (first-generation kernel), then generic.
+int launch_block_match_ldg(const BlockMatchParams& p, cudaStream_t stream, uint64_t* launches);
 // Forces the generic (untuned) kernel; used by tests to cross-check the tuned instances.
 int launch_block_match_generic(const BlockMatchParams& p, cudaStream_t stream, uint64_t* launches);
 

@@ -33,12 +33,17 @@ def run(ctx, w, h, block, search, n_pairs, iters=20, metric=0):
 if __name__ == "__main__":
     ctx = capi.Context(0)
     print(capi.version(), ctx.device_info())
-    run(ctx, 1920, 1080, 16, 16, 1)
-    run(ctx, 1920, 1080, 16, 16, 8)
-    run(ctx, 1920, 1080, 16, 16, 64)
-    run(ctx, 1920, 1080, 16, 16, 64, metric=1)
-    run(ctx, 640, 360, 16, 8, 64)
-    run(ctx, 3840, 2160, 8, 32, 8)
-    run(ctx, 7680, 4320, 16, 16, 4)
-    ctx.set_option("block_match_kernel", 1)
-    run(ctx, 1920, 1080, 16, 16, 4, iters=3)
+    for opt, name in ((0, "tma"), (3, "tma-alt"), (2, "ldg-tile")):
+        ctx.set_option("block_match_kernel", opt)
+        print("== kernel", name)
+        run(ctx, 1920, 1080, 16, 16, 1)
+        run(ctx, 1920, 1080, 16, 16, 64)
+        if opt == 3:
+            continue
+        run(ctx, 1920, 1080, 16, 16, 64, metric=1)
+        run(ctx, 640, 360, 16, 8, 64)
+        run(ctx, 3840, 2160, 8, 32, 8)
+        run(ctx, 3840, 2160, 16, 32, 8)
+        run(ctx, 1920, 1080, 8, 16, 16)
+        run(ctx, 1920, 1080, 8, 8, 16)
+        run(ctx, 7680, 4320, 16, 16, 4)
