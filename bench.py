@@ -45,7 +45,8 @@ WORKLOAD = "1080p block matching 16x16/+-16 SAD, 65-frame synthetic stream = 64 
 BYTES_PER_PAIR = 2 * W * H + 16 * NBLOCKS
 ABSDIFF_PER_PAIR = NBLOCKS * (2 * SEARCH + 1) ** 2 * BLOCK * BLOCK
 # ncu --set full capture of block_match_tile_kernel (profiles/): dram bytes read+write per launch
-NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+# measured: 35.25 MB for a 17-frame capture = every frame read exactly once, writes stay in L2 (profiles/r1_block_match_ncu.md)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = (PAIRS + 1) * W * H
 
 
 def _peaks():
@@ -85,7 +86,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
+                time.sleep(0.005)
         except Exception as e:  # NVML unavailable: report that instead of inventing clocks
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -249,7 +250,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
-                         "kernel": "block_match_tile_kernel<16,16>", "bytes_per_launch": BYTES_PER_PAIR * PAIRS,
+                         "kernel": "block_match_tma_kernel<16,16,17,4,288,SAD>", "bytes_per_launch": BYTES_PER_PAIR * PAIRS,
                          "kernel_ms": launch_s * 1e3,
                          "alu": {"bound": "int-alu (VABSDIFF4, exhaustive SAD is ~540 ops/byte)", "achieved": alu_ach,
                                  "peak": alu_peak, "unit": "T absdiff/s", "frac": alu_ach / alu_peak}},
