@@ -71,6 +71,10 @@ int ofpsb_sync(ofpsb_ctx *ctx);
 int ofpsb_device_info(ofpsb_ctx *ctx, int *sm_count, size_t *l2_bytes, size_t *mem_bytes, int *cc_major, int *cc_minor);
 /* Number of kernels launched by this context since creation (for gpu_launches accounting). */
 uint64_t ofpsb_launch_count(ofpsb_ctx *ctx);
+/* Counters of the LAST pruned block-match launch (needs option "block_match_stats" = 1; synchronises):
+ * out[0] = blocks seen, out[1] = blocks decided by the pruning pass, out[2] = exact SAD evaluations it
+ * spent, out[3] = blocks sent to the exhaustive work list. */
+int ofpsb_block_match_stats(ofpsb_ctx *ctx, uint64_t out[4]);
 /* The stream the context currently enqueues on (a cudaStream_t), for event timing by the caller. */
 void *ofpsb_get_stream(ofpsb_ctx *ctx);
 /* Tuning / test knobs; unknown keys return OFPSB_E_INVALID.
@@ -78,7 +82,10 @@ void *ofpsb_get_stream(ofpsb_ctx *ctx);
  *   "block_match_kernel"  0 = best instance (TMA-staged, else LDG-staged, else generic; default),
  *                         1 = force the generic kernel, 2 = force the LDG-staged tile kernel,
  *                         3 = TMA-staged, alternative tile shape
- *   "batch_chunk_pairs"   pairs per pipelined chunk in ofpsb_block_match_batch (0 = automatic) */
+ *   "batch_chunk_pairs"   pairs per pipelined chunk in ofpsb_block_match_batch (0 = automatic)
+ *   "block_match_prune"   1 = exact successive-elimination pruning in front of the exhaustive SAD search
+ *                         (default; same results, data-dependent speed), 0 = always exhaustive
+ *   "block_match_stats"   1 = count blocks / decided blocks / exact evaluations of the pruning pass */
 int ofpsb_set_option(ofpsb_ctx *ctx, const char *key, long long value);
 
 /* Pinned host memory (page-locked; makes the batched host entry points copy asynchronously) and

@@ -40,6 +40,7 @@ SIGNATURES = {
     "ofpsb_device_info": (C.c_int, [_vp, _intp, _szp, _szp, _intp, _intp]),
     "ofpsb_launch_count": (C.c_uint64, [_vp]),
     "ofpsb_set_option": (C.c_int, [_vp, C.c_char_p, C.c_longlong]),
+    "ofpsb_block_match_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "ofpsb_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "ofpsb_host_free": (None, [_vp]),
     "ofpsb_dev_alloc": (C.c_int, [_vp, C.POINTER(_vp), C.c_size_t]),
@@ -191,6 +192,11 @@ class Context:
 
     def set_option(self, key: str, value: int):
         check(lib().ofpsb_set_option(self._h, key.encode(), int(value)))
+
+    def block_match_stats(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        check(lib().ofpsb_block_match_stats(self._h, out))
+        return {"blocks": out[0], "decided": out[1], "exact_evals": out[2], "worklist": out[3]}
 
     def launch_count(self) -> int:
         return int(lib().ofpsb_launch_count(self._h))

@@ -146,7 +146,13 @@ int launch_bm(ofpsb_ctx* ctx, const BlockMatchParams& p)
         if (p.mv_xy) q.mv_xy = p.mv_xy + 2 * nb * first;
         if (p.cost) q.cost = p.cost + nb * first;
         if (p.entries) q.entries = p.entries + nb * first;
-        int rc;
+        int rc = 1;
+        if (ctx->opt_block_match_prune && ctx->opt_block_match_kernel == 0)
+            rc = launch_block_match_pruned(q, ctx->bm_scratch, ctx->sm_count, ctx->stream, &ctx->launches);
+        if (rc != 1) {
+            if (rc) return rc;
+            continue;
+        }
         switch (ctx->opt_block_match_kernel) {
             case 1: rc = launch_block_match_generic(q, ctx->stream, &ctx->launches); break;
             case 2: rc = launch_block_match_ldg(q, ctx->stream, &ctx->launches); break;
@@ -279,7 +285,7 @@ void ofpsb_destroy(ofpsb_ctx* ctx)
     DevBuf* bufs[] = {&ctx->d_frames, &ctx->d_mv, &ctx->d_cost, &ctx->d_entries, &ctx->d_field, &ctx->d_field2,
                       &ctx->d_counts, &ctx->d_misc, &ctx->d_detect_scratch, &ctx->densify.keys_a, &ctx->densify.keys_b,
                       &ctx->densify.vals_a, &ctx->densify.vals_b, &ctx->densify.hist, &ctx->densify.cell_start,
-                      &ctx->densify.sums, &ctx->almeida.state, &ctx->almeida.partial, &ctx->almeida.hyp,
+                      &ctx->densify.sums, &ctx->bm_scratch.sums, &ctx->bm_scratch.worklist, &ctx->almeida.state, &ctx->almeida.partial, &ctx->almeida.hyp,
                       &ctx->almeida.inlier_idx, &ctx->almeida.flags};
     for (DevBuf* b : bufs) b->release();
     ctx->h_misc.release();
@@ -326,6 +332,25 @@ int ofpsb_device_info(ofpsb_ctx* ctx, int* sm_count, size_t* l2_bytes, size_t* m
 
 uint64_t ofpsb_launch_count(ofpsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int ofpsb_block_match_stats(ofpsb_ctx* ctx, uint64_t out[4])
+{
+    OFPSB_ENTER(ctx);
+    if (!out) {
+        set_error("block_match_stats: null output");
+        return OFPSB_E_INVALID;
+    }
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (!ctx->bm_scratch.worklist.ptr) return OFPSB_OK;
+    OFPSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    unsigned char raw[64];
+    OFPSB_CUDA_TRY(cudaMemcpy(raw, ctx->bm_scratch.worklist.ptr, 64, cudaMemcpyDeviceToHost));
+    uint32_t cnt;
+    memcpy(&cnt, raw, 4);
+    memcpy(out, raw + 8, 24);
+    out[3] = cnt;
+    return OFPSB_OK;
+}
+
 int ofpsb_set_option(ofpsb_ctx* ctx, const char* key, long long value)
 {
     if (!ctx || !key) {
@@ -335,6 +360,8 @@ int ofpsb_set_option(ofpsb_ctx* ctx, const char* key, long long value)
     if (!strcmp(key, "densify_path") && value >= 0 && value <= 2) ctx->opt_densify_path = (int)value;
     else if (!strcmp(key, "block_match_kernel") && value >= 0 && value <= 3) ctx->opt_block_match_kernel = (int)value;
     else if (!strcmp(key, "batch_chunk_pairs") && value >= 0 && value <= 65535) ctx->opt_batch_chunk_pairs = (int)value;
+    else if (!strcmp(key, "block_match_prune") && value >= 0 && value <= 1) ctx->opt_block_match_prune = (int)value;
+    else if (!strcmp(key, "block_match_stats") && value >= 0 && value <= 1) ctx->bm_scratch.collect_stats = value != 0;
     else {
         set_error("set_option: unknown key or value out of range: %s = %lld", key, value);
         return OFPSB_E_INVALID;

@@ -63,6 +63,15 @@ struct BlockMatchParams {
 // Launches the block matcher (tuned template instance if one exists for (block, range),
 // otherwise the generic kernel).  Returns 0 or OFPSB_E_*; *launches += kernels launched.
 int launch_block_match(const BlockMatchParams& p, cudaStream_t stream, uint64_t* launches, int variant = 0);
+// Scratch of the pruned search (block_match_prune.cu): window-sum planes and the work list.
+struct BlockMatchScratch {
+    DevBuf sums, worklist;
+    bool collect_stats = false;
+};
+// Exact pruned SAD search (window-sum bounds + exhaustive search of the undecided blocks only).
+// Returns 0 when launched, 1 when the path does not apply, < 0 on error.
+int launch_block_match_pruned(const BlockMatchParams& p, BlockMatchScratch& scratch, int sm_count, cudaStream_t stream,
+                              uint64_t* launches);
 // TMA-staged instances (block_match_tma.cu).  Returns 0 when launched, 1 when no instance applies
 // (geometry, or base / strides not 16-byte aligned), < 0 on error.
 int launch_block_match_tma(const BlockMatchParams& p, cudaStream_t stream, int variant);
@@ -119,6 +128,8 @@ struct ofpsb_ctx {
     int opt_densify_path = 0;
     int opt_block_match_kernel = 0;
     int opt_batch_chunk_pairs = 0;
+    int opt_block_match_prune = 1;
+    ofpsb::BlockMatchScratch bm_scratch;
     // scratch
     ofpsb::DevBuf d_frames, d_mv, d_cost, d_entries, d_field, d_field2, d_counts, d_misc, d_detect_scratch;
     ofpsb::PinBuf h_misc;

@@ -149,3 +149,44 @@ def test_invalid_arguments(ctx):
         ctx.block_match(prev, prev, 6, 4, 0)        # block not a multiple of 4
     with pytest.raises(capi.OfpsError):
         ctx.block_match(prev, prev, 16, 4, 7)       # unknown metric
+
+
+@pytest.mark.parametrize("noise", [0, 1, 3])
+@pytest.mark.parametrize("block,search,w,h", [(16, 16, 1920, 1080), (8, 32, 768, 432), (16, 8, 640, 360), (8, 8, 320, 208),
+                                              (16, 32, 640, 368), (8, 16, 648, 360)])
+def test_pruned_equals_exhaustive(ctx, oracle, block, search, w, h, noise):
+    """The successive-elimination front end must not change a single output bit."""
+    prev, cur, _ = synth.make_pair(w, h, search, index=11 + noise, noise_lsb=noise)
+    ctx.set_option("block_match_stats", 1)
+    try:
+        a = ctx.block_match(prev, cur, block, search, 0)
+        st = ctx.block_match_stats()
+        ctx.set_option("block_match_prune", 0)
+        b = ctx.block_match(prev, cur, block, search, 0)
+    finally:
+        ctx.set_option("block_match_prune", 1)
+        ctx.set_option("block_match_stats", 0)
+    for k in ("mv", "cost", "entries"):
+        np.testing.assert_array_equal(a[k], b[k])
+    if w % 16 == 0:     # the pruned path needs 16-byte aligned rows (TMA); otherwise it is skipped
+        assert st["blocks"] == a["n_blocks"] and st["decided"] + st["worklist"] == st["blocks"]
+    if noise == 0 and w % 16 == 0:
+        assert st["decided"] > 0.5 * st["blocks"]       # noise-free synthetic motion is mostly decided by bounds
+    mv, cost, _ = oracle.block_match(prev, cur, block, search, 0, threads=oracle.max_threads(), fast=True)
+    np.testing.assert_array_equal(a["mv"], mv)
+    np.testing.assert_array_equal(a["cost"], cost)
+
+
+def test_pruned_batch_and_worst_case(ctx, oracle):
+    """Unrelated frames (nothing decided by the bounds) and a batch through the work list."""
+    rng = np.random.default_rng(5)
+    prev = rng.integers(0, 256, (3, 208, 336), dtype=np.uint8)
+    cur = rng.integers(0, 256, (3, 208, 336), dtype=np.uint8)
+    cur[1] = prev[1]                                    # one pair fully static
+    got = ctx.block_match(prev, cur, 16, 16, 0)
+    for i in range(3):
+        mv, cost, ent = oracle.block_match(prev[i], cur[i], 16, 16, 0)
+        np.testing.assert_array_equal(got["mv"][i], mv)
+        np.testing.assert_array_equal(got["cost"][i], cost)
+        assert got["entries"][i].tobytes() == ent.tobytes()
+    assert not got["mv"][1].any()
