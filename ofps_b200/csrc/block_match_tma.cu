@@ -19,16 +19,14 @@
 //     block with two REDUX.MIN passes over shared memory.
 // The result is bit-identical to the generic kernel and the oracle (same tie-break:
 // lexicographic (cost, dx^2+dy^2, dy, dx)).
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
-#include "block_match_common.cuh"
+#include "tma_common.cuh"
 
 namespace ofpsb {
 
 namespace {
 
 using namespace bm;
+using namespace tma;
 
 template <int B, int R, int G, int TBX, int NT>
 struct TmaCfg {
@@ -61,16 +59,6 @@ struct TmaCfg {
     static_assert(ND <= 127 && 2 * (NG * G - R) < 128, "key fields: 7-bit dy rank, 7-bit dx/dy indices");
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
-        : "memory");
-}
-
 // cost * 128 + rank on the FMA pipe (IMAD): the ALU pipe is the one the SAD instruction saturates
 __device__ __forceinline__ uint32_t fold_key(uint32_t cost, uint32_t rank)
 {
@@ -85,17 +73,6 @@ struct TileLimits {
     int dx_lo, dx_hi, dy_lo, dy_hi;
     int xadj;   // bytes between the 16-byte aligned TMA box origin and the block's window origin (0 or 8)
 };
-
-__device__ __forceinline__ void mbar_wait(uint32_t b32, uint32_t parity)
-{
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
-                     : "=r"(done)
-                     : "r"(b32), "r"(parity)
-                     : "memory");
-    }
-}
 
 // The SAD work of one tile: every thread takes items (dy group, shift class, block, dx/4), walks its
 // window column once and leaves (cost, position code) of its best candidate in shared memory.
@@ -304,8 +281,9 @@ __global__ void __launch_bounds__(NT) block_match_list_kernel(const __grid_const
     uint32_t* r_cost = curs + C::CUR_BYTES / 4;
     uint32_t* r_pos = r_cost + C::SLOTS;
     uint64_t* bar = reinterpret_cast<uint64_t*>(r_pos + C::SLOTS);
-    __shared__ TileLimits lim[TBX];
-    __shared__ uint32_t s_blk[TBX];
+    __shared__ TileLimits lim[2][TBX];
+    __shared__ uint32_t s_blk[2][TBX];
+    static_assert(TBX <= 32, "tile set-up is done by one warp");
 
     const int tid = threadIdx.x;
     const uint32_t count = *list_count;
@@ -315,43 +293,55 @@ __global__ void __launch_bounds__(NT) block_match_list_kernel(const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+
+    // Warp 0 describes a tile (block coordinates, candidate limits) and starts its TMA loads into the raw
+    // staging area; called for tile i+1 as soon as the layout pass of tile i has consumed the staging area,
+    // so the loads run behind the SAD loop of tile i.
+    auto start_tile = [&](uint32_t tile, int slot) {
+        if (tid < 32) {
+            if (tid < TBX) {
+                const uint32_t li = tile * TBX + tid;
+                TileLimits L = {0, -1, 0, -1, 0};
+                uint32_t gb = 0xFFFFFFFFu;
+                if (li < count) {
+                    gb = list[li];
+                    const uint32_t rem = gb % nblk;
+                    const int by = (int)(rem / p.nbx), bx = (int)(rem % p.nbx);
+                    const int y0 = by * B;
+                    L.dy_lo = max(-R, -p.halo_top - y0);
+                    L.dy_hi = min(R, p.strip_h + p.halo_bottom - B - y0);
+                    L.dx_lo = max(-R, -bx * B);
+                    L.dx_hi = min(R, p.w - B - bx * B);
+                    L.xadj = (bx * B) & 15;
+                }
+                lim[slot][tid] = L;
+                s_blk[slot][tid] = gb;
+            }
+            __syncwarp();
+            if (tid == 0) {
+                const uint32_t b32 = smem_u32(bar);
+                uint32_t nvalid = 0;
+                for (int b = 0; b < TBX; b++) nvalid += s_blk[slot][b] != 0xFFFFFFFFu;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(nvalid * C::TX_PER_BLOCK) : "memory");
+                for (int b = 0; b < TBX; b++) {
+                    const uint32_t gb = s_blk[slot][b];
+                    if (gb == 0xFFFFFFFFu) continue;
+                    const int pair = (int)(gb / nblk);
+                    const uint32_t rem = gb % nblk;
+                    const int by = (int)(rem / p.nbx), bx = (int)(rem % p.nbx);
+                    const int xa = (bx * B) & ~15;   // TMA boxes start on a 16-byte boundary
+                    tma_load_3d(smem_u32(raw_win + b * C::RAW_WIN_BYTES), &map_prev, xa - C::RA, by * B - R + p.halo_top, pair, b32);
+                    tma_load_3d(smem_u32(raw_cur + b * C::RAW_CUR_BYTES), &map_cur, xa, by * B, pair, b32);
+                }
+            }
+        }
+    };
+
     uint32_t parity = 0;
-    for (uint32_t tile = blockIdx.x; (unsigned long long)tile * TBX < count; tile += gridDim.x) {
-        if (tid < TBX) {
-            const uint32_t li = tile * TBX + tid;
-            TileLimits L = {0, -1, 0, -1, 0};
-            uint32_t gb = 0xFFFFFFFFu;
-            if (li < count) {
-                gb = list[li];
-                const uint32_t rem = gb % nblk;
-                const int by = (int)(rem / p.nbx), bx = (int)(rem % p.nbx);
-                const int y0 = by * B;
-                L.dy_lo = max(-R, -p.halo_top - y0);
-                L.dy_hi = min(R, p.strip_h + p.halo_bottom - B - y0);
-                L.dx_lo = max(-R, -bx * B);
-                L.dx_hi = min(R, p.w - B - bx * B);
-                L.xadj = (bx * B) & 15;
-            }
-            lim[tid] = L;
-            s_blk[tid] = gb;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t b32 = smem_u32(bar);
-            uint32_t nvalid = 0;
-            for (int b = 0; b < TBX; b++) nvalid += s_blk[b] != 0xFFFFFFFFu;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(nvalid * C::TX_PER_BLOCK) : "memory");
-            for (int b = 0; b < TBX; b++) {
-                const uint32_t gb = s_blk[b];
-                if (gb == 0xFFFFFFFFu) continue;
-                const int pair = (int)(gb / nblk);
-                const uint32_t rem = gb % nblk;
-                const int by = (int)(rem / p.nbx), bx = (int)(rem % p.nbx);
-                const int xa = (bx * B) & ~15;   // TMA boxes start on a 16-byte boundary
-                tma_load_3d(smem_u32(raw_win + b * C::RAW_WIN_BYTES), &map_prev, xa - C::RA, by * B - R + p.halo_top, pair, b32);
-                tma_load_3d(smem_u32(raw_cur + b * C::RAW_CUR_BYTES), &map_cur, xa, by * B, pair, b32);
-            }
-        }
+    int slot = 0;
+    if ((unsigned long long)blockIdx.x * TBX < count) start_tile(blockIdx.x, 0);
+    __syncthreads();
+    for (uint32_t tile = blockIdx.x; (unsigned long long)tile * TBX < count; tile += gridDim.x, slot ^= 1) {
         mbar_wait(smem_u32(bar), parity);
         parity ^= 1;
         // lay out the four byte-shifted window copies [s][row][b][word] and the current tile [row][b][word]
@@ -373,16 +363,18 @@ __global__ void __launch_bounds__(NT) block_match_list_kernel(const __grid_const
             const int rem = idx - b * (B * C::WCOLS);
             const int row = rem / C::WCOLS, k = rem - row * C::WCOLS;
             curs[row * C::CUR_ROW_WORDS + b * C::WCOLS + k] =
-                reinterpret_cast<const uint32_t*>(raw_cur + b * C::RAW_CUR_BYTES)[row * (C::CBOX_W / 4) + k + (lim[b].xadj >> 2)];
+                reinterpret_cast<const uint32_t*>(raw_cur + b * C::RAW_CUR_BYTES)[row * (C::CBOX_W / 4) + k + (lim[slot][b].xadj >> 2)];
         }
-        __syncthreads();
+        __syncthreads();   // staging consumed: the next tile's loads may overwrite it
+        const uint32_t next = tile + gridDim.x;
+        if ((unsigned long long)next * TBX < count) start_tile(next, slot ^ 1);
 
-        tile_items<C, B, R, G, TBX, NT, METRIC, C::WBOX_W>(win, curs, lim, r_cost, r_pos, tid);
+        tile_items<C, B, R, G, TBX, NT, METRIC, C::WBOX_W>(win, curs, lim[slot], r_cost, r_pos, tid);
         __syncthreads();
 
         const int warp = tid >> 5, lane = tid & 31;
         for (int blk = warp; blk < TBX; blk += NT / 32) {
-            const uint32_t gb = s_blk[blk];
+            const uint32_t gb = s_blk[slot][blk];
             if (gb == 0xFFFFFFFFu) continue;
             const unsigned long long key = block_argmin<C>(r_cost + blk * C::NG * C::ND, r_pos + blk * C::NG * C::ND, lane);
             if (lane == 0) {
@@ -390,39 +382,8 @@ __global__ void __launch_bounds__(NT) block_match_list_kernel(const __grid_const
                 write_block_outputs(p, (size_t)gb, key, (int)(rem % p.nbx), (int)(rem / p.nbx));
             }
         }
-        __syncthreads();   // results and staging are reused by the next tile
+        __syncthreads();   // results are reused by the next tile
     }
-}
-
-PFN_cuTensorMapEncodeTiled get_encode()
-{
-    static PFN_cuTensorMapEncodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(ptr);
-    }
-    return fn;
-}
-
-// u8 tensor (x: w valid bytes of each `stride`-byte row, y: rows, z: pairs)
-bool make_map(CUtensorMap* map, const uint8_t* base, int w, int rows, long long stride, long long pair_stride, int pairs,
-              int box_w, int box_h)
-{
-    PFN_cuTensorMapEncodeTiled enc = get_encode();
-    if (!enc) return false;
-    if (pairs <= 1 || pair_stride <= 0) pair_stride = ((stride * (long long)rows) + 15) & ~15ll;
-    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)rows, (cuuint64_t)(pairs > 0 ? pairs : 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)stride, (cuuint64_t)pair_stride};
-    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int B, int R, int G, int TBX, int NT>
