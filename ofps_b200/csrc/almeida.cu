@@ -533,7 +533,7 @@ void make_const(float aspect, float fov_y_deg, AlmeidaConst& c)
     c.fx = c.fy / aspect;
 }
 
-constexpr size_t SINGLE_MAX = 16384;   // entries handled by the one-CTA solver
+constexpr size_t SINGLE_MAX = 2048;    // entries handled by the one-CTA solver (above: one launch per iteration)
 
 int run_lsq(const ofps_mv* d_entries, const uint32_t* d_idx, size_t n, const uint32_t* d_n_ptr, const AlmeidaConst& cst,
             float* d_quat, AlmeidaScratch& s, int sm_count, cudaStream_t stream, uint64_t* launches)

@@ -193,21 +193,23 @@ int detect_from_device_entries(ofpsb_ctx* ctx, const ofps_mv* d_entries, size_t 
         set_error("detect_block_motion: field buffer holds %zu cells, %zu needed", field_cap_cells, cells);
         return OFPSB_E_CAPACITY;
     }
+    // island field and result record live back to back so that one D2H copy (into pinned memory) returns both
+    const size_t rec = (sizeof(DetectResult) + 15) & ~(size_t)15;
     if (int rc = ctx->d_field.reserve(cells * 8)) return rc;
-    if (int rc = ctx->d_field2.reserve(cells * 8)) return rc;
-    if (int rc = ctx->d_misc.reserve(sizeof(DetectResult))) return rc;
-    if (int rc = ctx->h_misc.reserve(sizeof(DetectResult))) return rc;
+    if (int rc = ctx->d_field2.reserve(rec + cells * 8)) return rc;
+    if (int rc = ctx->h_misc.reserve(rec + cells * 8)) return rc;
+    DetectResult* d_res = ctx->d_field2.as<DetectResult>();
+    float* d_island = reinterpret_cast<float*>(ctx->d_field2.as<char>() + rec);
     if (int rc = launch_densify(d_entries, n, dim, dim, ctx->d_field.as<float>(), nullptr, ctx->densify, ctx->stream,
                                 &ctx->launches, ctx->opt_densify_path))
         return rc;
-    if (int rc = launch_detect(ctx->d_field.as<float>(), dim, target_motion, min_size, ctx->d_field2.as<float>(),
-                               ctx->d_misc.as<DetectResult>(), ctx->d_detect_scratch, ctx->stream, &ctx->launches))
+    if (int rc = launch_detect(ctx->d_field.as<float>(), dim, target_motion, min_size, d_island, d_res,
+                               ctx->d_detect_scratch, ctx->stream, &ctx->launches))
         return rc;
-    OFPSB_CUDA_TRY(cudaMemcpyAsync(ctx->h_misc.ptr, ctx->d_misc.ptr, sizeof(DetectResult), cudaMemcpyDeviceToHost,
+    OFPSB_CUDA_TRY(cudaMemcpyAsync(ctx->h_misc.ptr, d_res, field_xy ? rec + cells * 8 : rec, cudaMemcpyDeviceToHost,
                                    ctx->stream));
-    if (field_xy)
-        OFPSB_CUDA_TRY(cudaMemcpyAsync(field_xy, ctx->d_field2.ptr, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
     OFPSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (field_xy) memcpy(field_xy, ctx->h_misc.as<char>() + rec, cells * 8);
     const DetectResult* r = ctx->h_misc.as<DetectResult>();
     if (has_motion) *has_motion = r->has_motion;
     if (area) *area = r->area;

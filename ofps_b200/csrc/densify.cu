@@ -67,25 +67,30 @@ __global__ void __launch_bounds__(256) densify_scan_kernel(const ofps_mv* __rest
     const float wm1 = (float)(unsigned long long)(gw - 1), hm1 = (float)(unsigned long long)(gh - 1);
     float sx = 0.0f, sy = 0.0f, cx = F32_EPSILON, cy = F32_EPSILON;
     const float4* e4 = reinterpret_cast<const float4*>(entries);
-    for (size_t base = 0; base < n; base += 32) {
-        const size_t i = base + lane;
-        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool hit = false;
-        if (i < n) {
-            e = __ldg(e4 + i);
-            hit = cell_of(e.x, e.y, wm1, hm1, gw) == cell;
+    constexpr int DEPTH = 8;   // independent 16-byte loads in flight per lane: the scan is latency-bound otherwise
+    for (size_t base = 0; base < n; base += 32 * DEPTH) {
+        float4 e[DEPTH];
+#pragma unroll
+        for (int k = 0; k < DEPTH; k++) {
+            const size_t i = base + (size_t)k * 32 + lane;
+            e[k] = i < n ? __ldg(e4 + i) : make_float4(-1.f, -1.f, 0.f, 0.f);
         }
-        unsigned m = __ballot_sync(0xffffffffu, hit);
-        while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            const float mx = __shfl_sync(0xffffffffu, e.z, l);
-            const float my = __shfl_sync(0xffffffffu, e.w, l);
-            // add_vector_idx (motion_field.rs:141-147), weight = 1
-            cx = __fadd_rn(cx, 1.0f);
-            cy = __fadd_rn(cy, 1.0f);
-            sx = __fadd_rn(__fmul_rn(mx, 1.0f), sx);
-            sy = __fadd_rn(__fmul_rn(my, 1.0f), sy);
+#pragma unroll
+        for (int k = 0; k < DEPTH; k++) {
+            const size_t i = base + (size_t)k * 32 + lane;
+            const bool hit = i < n && cell_of(e[k].x, e[k].y, wm1, hm1, gw) == cell;
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {   // fold the hits in lane (= input) order
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const float mx = __shfl_sync(0xffffffffu, e[k].z, l);
+                const float my = __shfl_sync(0xffffffffu, e[k].w, l);
+                // add_vector_idx (motion_field.rs:141-147), weight = 1
+                cx = __fadd_rn(cx, 1.0f);
+                cy = __fadd_rn(cy, 1.0f);
+                sx = __fadd_rn(__fmul_rn(mx, 1.0f), sx);
+                sy = __fadd_rn(__fmul_rn(my, 1.0f), sy);
+            }
         }
     }
     if (lane == 0) finish_cell(sx, sy, cx, cy, cell, field, counts);

@@ -61,9 +61,9 @@ def test_dense_1080p_recovers_truth(ctx, oracle):
         q = ctx.almeida(field, 16 / 9, 22.275)
         assert quat_close(q, q_truth) < TOL, (euler, q, q_truth)
     # multi-CTA path == single-CTA path on the same data (both deterministic)
-    sub = field[:16384]
+    sub = field[:2048]
     a = ctx.almeida(sub, 16 / 9, 22.275)
-    b = ctx.almeida(field[:16385], 16 / 9, 22.275)
+    b = ctx.almeida(field[:2049], 16 / 9, 22.275)
     assert quat_close(a, b) < 1e-5
     assert np.array_equal(ctx.almeida(field, 16 / 9, 22.275), ctx.almeida(field, 16 / 9, 22.275))
 
