@@ -85,7 +85,8 @@ void *ofpsb_get_stream(ofpsb_ctx *ctx);
  *   "batch_chunk_pairs"   pairs per pipelined chunk in ofpsb_block_match_batch (0 = automatic)
  *   "block_match_prune"   1 = exact successive-elimination pruning in front of the exhaustive SAD search
  *                         (default; same results, data-dependent speed), 0 = always exhaustive
- *   "block_match_stats"   1 = count blocks / decided blocks / exact evaluations of the pruning pass */
+ *   "block_match_stats"   1 = count blocks / decided blocks / exact evaluations of the pruning pass
+ *   "block_match_chunk_pairs"  pairs per chunk of the pruned path (0 = whole batch in one chunk, default) */
 int ofpsb_set_option(ofpsb_ctx *ctx, const char *key, long long value);
 
 /* Pinned host memory (page-locked; makes the batched host entry points copy asynchronously) and
@@ -135,6 +136,14 @@ int ofpsb_block_match_strip_dev(ofpsb_ctx *ctx, const uint8_t *d_prev, const uin
                                 int stride, int halo_top, int halo_bottom, int y_offset, int full_h,
                                 int block, int range, int metric,
                                 int16_t *d_mv_xy, uint32_t *d_cost, ofps_mv *d_entries);
+
+/* Batched strip: n_pairs pairs of one strip, pair i at d_prev + i*pair_stride / d_cur + i*pair_stride (for a
+ * stream stored as [halo_top | strip | halo_bottom] rows per frame, d_cur = d_prev + pair_stride).  Outputs
+ * are n_pairs * (w/block)*(strip_h/block) long. */
+int ofpsb_block_match_strip_batch_dev(ofpsb_ctx *ctx, const uint8_t *d_prev, const uint8_t *d_cur, int w, int strip_h,
+                                      int stride, size_t pair_stride, int n_pairs, int halo_top, int halo_bottom,
+                                      int y_offset, int full_h, int block, int range, int metric,
+                                      int16_t *d_mv_xy, uint32_t *d_cost, ofps_mv *d_entries);
 
 /* -------------------------------------------------------------- densifier
  * field_xy: gw*gh*2 floats, cell-major [x0,y0,x1,y1,...], cell = y*gw+x

@@ -55,6 +55,8 @@ SIGNATURES = {
                                         C.c_int, C.c_int, _vp, _vp, _vp]),
     "ofpsb_block_match_strip_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "ofpsb_block_match_strip_batch_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "ofpsb_densify": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp]),
     "ofpsb_densify_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp]),
     "ofpsb_block_dim": (C.c_int, [C.c_float, C.c_size_t, _szp]),
@@ -271,6 +273,13 @@ class Context:
         check(lib().ofpsb_block_match_strip_dev(self._h, _ptr(d_prev), _ptr(d_cur), w, strip_h, stride, halo_top,
                                                 halo_bottom, y_offset, full_h, block, search, metric, _ptr(d_mv),
                                                 _ptr(d_cost), _ptr(d_entries)))
+
+    def block_match_strip_batch_dev(self, d_prev, d_cur, w: int, strip_h: int, stride: int, pair_stride: int, n_pairs: int,
+                                    halo_top: int, halo_bottom: int, y_offset: int, full_h: int, block: int, search: int,
+                                    metric: int, d_mv=None, d_cost=None, d_entries=None):
+        check(lib().ofpsb_block_match_strip_batch_dev(self._h, _ptr(d_prev), _ptr(d_cur), w, strip_h, stride, pair_stride,
+                                                      n_pairs, halo_top, halo_bottom, y_offset, full_h, block, search,
+                                                      metric, _ptr(d_mv), _ptr(d_cost), _ptr(d_entries)))
 
     # ---- densifier / detector
     def densify(self, entries, gw: int, gh: int, return_counts: bool = False):

@@ -265,6 +265,7 @@ int ofpsb_create(int device, ofpsb_ctx** out)
     ctx->cc_major = prop.major;
     ctx->cc_minor = prop.minor;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    ctx->bm_scratch.l2_bytes = ctx->l2_bytes;
     ctx->mem_bytes = prop.totalGlobalMem;
     cudaError_t e1 = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
@@ -349,7 +350,8 @@ int ofpsb_block_match_stats(ofpsb_ctx* ctx, uint64_t out[4])
     uint32_t cnt;
     memcpy(&cnt, raw, 4);
     memcpy(out, raw + 8, 24);
-    out[3] = cnt;
+    (void)cnt;
+    out[3] = out[0] - out[1];
     return OFPSB_OK;
 }
 
@@ -364,6 +366,7 @@ int ofpsb_set_option(ofpsb_ctx* ctx, const char* key, long long value)
     else if (!strcmp(key, "batch_chunk_pairs") && value >= 0 && value <= 65535) ctx->opt_batch_chunk_pairs = (int)value;
     else if (!strcmp(key, "block_match_prune") && value >= 0 && value <= 1) ctx->opt_block_match_prune = (int)value;
     else if (!strcmp(key, "block_match_stats") && value >= 0 && value <= 1) ctx->bm_scratch.collect_stats = value != 0;
+    else if (!strcmp(key, "block_match_chunk_pairs") && value >= 0 && value <= 32768) ctx->bm_scratch.chunk_pairs = (int)value;
     else {
         set_error("set_option: unknown key or value out of range: %s = %lld", key, value);
         return OFPSB_E_INVALID;
@@ -441,14 +444,15 @@ int ofpsb_block_match_dev(ofpsb_ctx* ctx, const uint8_t* d_prev, const uint8_t* 
     return launch_bm(ctx, p);
 }
 
-int ofpsb_block_match_strip_dev(ofpsb_ctx* ctx, const uint8_t* d_prev, const uint8_t* d_cur, int w, int strip_h,
-                                int stride, int halo_top, int halo_bottom, int y_offset, int full_h, int block,
-                                int range, int metric, int16_t* d_mv_xy, uint32_t* d_cost, ofps_mv* d_entries)
+int ofpsb_block_match_strip_batch_dev(ofpsb_ctx* ctx, const uint8_t* d_prev, const uint8_t* d_cur, int w, int strip_h,
+                                      int stride, size_t pair_stride, int n_pairs, int halo_top, int halo_bottom,
+                                      int y_offset, int full_h, int block, int range, int metric, int16_t* d_mv_xy,
+                                      uint32_t* d_cost, ofps_mv* d_entries)
 {
     OFPSB_ENTER(ctx);
     BlockMatchParams p;
-    if (int rc = fill_params(p, d_prev, d_cur, w, strip_h, stride, 0, 1, block, range, metric, d_mv_xy, d_cost,
-                             d_entries))
+    if (int rc = fill_params(p, d_prev, d_cur, w, strip_h, stride, pair_stride, n_pairs, block, range, metric, d_mv_xy,
+                             d_cost, d_entries))
         return rc;
     if (halo_top < 0 || halo_bottom < 0 || y_offset < 0 || full_h < y_offset + strip_h) {
         set_error("block_match_strip: bad strip placement (y_offset=%d strip_h=%d full_h=%d halos=%d/%d)", y_offset,
@@ -460,6 +464,14 @@ int ofpsb_block_match_strip_dev(ofpsb_ctx* ctx, const uint8_t* d_prev, const uin
     p.y_offset = y_offset;
     p.full_h = full_h;
     return launch_bm(ctx, p);
+}
+
+int ofpsb_block_match_strip_dev(ofpsb_ctx* ctx, const uint8_t* d_prev, const uint8_t* d_cur, int w, int strip_h,
+                                int stride, int halo_top, int halo_bottom, int y_offset, int full_h, int block,
+                                int range, int metric, int16_t* d_mv_xy, uint32_t* d_cost, ofps_mv* d_entries)
+{
+    return ofpsb_block_match_strip_batch_dev(ctx, d_prev, d_cur, w, strip_h, stride, 0, 1, halo_top, halo_bottom, y_offset,
+                                             full_h, block, range, metric, d_mv_xy, d_cost, d_entries);
 }
 
 int ofpsb_block_match_batch(ofpsb_ctx* ctx, const uint8_t* prev, const uint8_t* cur, int w, int h, int stride,

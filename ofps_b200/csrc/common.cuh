@@ -67,6 +67,8 @@ int launch_block_match(const BlockMatchParams& p, cudaStream_t stream, uint64_t*
 struct BlockMatchScratch {
     DevBuf sums, worklist;
     bool collect_stats = false;
+    int chunk_pairs = 0;      // pairs per pruned chunk (0 = whole batch; smaller chunks stay L2-resident but measured slower)
+    size_t l2_bytes = 0;
 };
 // Exact pruned SAD search (window-sum bounds + exhaustive search of the undecided blocks only).
 // Returns 0 when launched, 1 when the path does not apply, < 0 on error.

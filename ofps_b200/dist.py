@@ -186,3 +186,86 @@ class TiledBlockMatcher:
         out = [torch.empty_like(pad) for _ in range(self.world)]
         dist.all_gather(out, pad, group=self.group)
         return np.concatenate([o[:p.nby * self.nbx].cpu().numpy() for o, p in zip(out, self.plan)])
+
+
+class TiledStreamMatcher:
+    """Spatial tiling of a STREAM of large frames: rank r keeps its strip (plus halo rows) of all n_frames
+    frames; the halo rows of every frame are exchanged with the two neighbours in ONE grouped NCCL
+    send/recv per step, then a single batched strip launch matches all n_frames-1 pairs.  The exchange
+    latency that dominates a single tiled pair is amortised over the batch.
+
+    Buffer layout per frame: [halo_top | own_rows | halo_bottom] rows of w bytes; pair i = frames (i, i+1),
+    so cur = prev + one frame buffer (the "stream" layout of ofpsb_block_match_strip_batch_dev)."""
+
+    def __init__(self, ctx, w: int, h: int, block: int, search: int, metric: int, n_frames: int, rank: int, world: int,
+                 group=None):
+        import torch
+        self.torch = torch
+        self.ctx, self.w, self.h, self.block, self.search, self.metric = ctx, w, h, block, search, metric
+        self.rank, self.world, self.group, self.n_frames = rank, world, group, n_frames
+        self.plan = strip_plan(h, block, search, world)
+        s = self.strip = self.plan[rank]
+        dev = torch.device("cuda", ctx.device)
+        self.nbx = w // block
+        self.rows = s.halo_top + s.own_rows + s.halo_bottom
+        self.frames = torch.zeros((n_frames, self.rows, w), dtype=torch.uint8, device=dev)
+        nb = s.nby * self.nbx
+        self.entries = torch.zeros((n_frames - 1, nb, 4), dtype=torch.float32, device=dev)
+        self.comm_stream = torch.cuda.Stream(device=dev)
+        self.kernel_stream = torch.cuda.ExternalStream(ctx.get_stream(), device=dev)
+
+    def load(self, frames: np.ndarray, fill_halos: bool = False):
+        """frames: [n_frames, h, w] uint8 on the host (every rank takes its rows)."""
+        torch, s = self.torch, self.strip
+        if fill_halos:
+            r0, r1 = s.y0 - s.halo_top, s.y0 + s.own_rows + s.halo_bottom
+            self.frames.copy_(torch.from_numpy(np.ascontiguousarray(frames[:, r0:r1])))
+        else:
+            own = torch.from_numpy(np.ascontiguousarray(frames[:, s.y0:s.y0 + s.own_rows]))
+            self.frames[:, s.halo_top:s.halo_top + s.own_rows].copy_(own)
+        torch.cuda.synchronize()
+
+    def exchange(self):
+        """One grouped send/recv with each neighbour for the halo rows of ALL frames."""
+        import torch.distributed as dist
+        s, plan, rank = self.strip, self.plan, self.rank
+        ops, recvs = [], []
+        own0, own1 = s.halo_top, s.halo_top + s.own_rows
+        if rank > 0:
+            up = plan[rank - 1]
+            if up.halo_bottom:
+                ops.append(dist.P2POp(dist.isend, self.frames[:, own0:own0 + up.halo_bottom].contiguous(), rank - 1, self.group))
+            if s.halo_top:
+                buf = self.torch.empty((self.n_frames, s.halo_top, self.w), dtype=self.torch.uint8, device=self.frames.device)
+                ops.append(dist.P2POp(dist.irecv, buf, rank - 1, self.group))
+                recvs.append((buf, 0, s.halo_top))
+        if rank + 1 < len(plan):
+            dn = plan[rank + 1]
+            if dn.halo_top:
+                ops.append(dist.P2POp(dist.isend, self.frames[:, own1 - dn.halo_top:own1].contiguous(), rank + 1, self.group))
+            if s.halo_bottom:
+                buf = self.torch.empty((self.n_frames, s.halo_bottom, self.w), dtype=self.torch.uint8, device=self.frames.device)
+                ops.append(dist.P2POp(dist.irecv, buf, rank + 1, self.group))
+                recvs.append((buf, own1, own1 + s.halo_bottom))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        for buf, a, b in recvs:
+            self.frames[:, a:b].copy_(buf)
+
+    def match(self):
+        s, w = self.strip, self.w
+        fb = self.rows * w
+        prev = self.frames.data_ptr() + s.halo_top * w
+        self.ctx.block_match_strip_batch_dev(prev, prev + fb, w, s.rows, w, fb, self.n_frames - 1, s.halo_top, s.halo_bottom,
+                                             s.y0, self.h, self.block, self.search, self.metric, None, None,
+                                             self.entries.data_ptr())
+
+    def run(self, exchange: bool = True):
+        torch = self.torch
+        if exchange and self.world > 1:
+            self.comm_stream.wait_stream(self.kernel_stream)
+            with torch.cuda.stream(self.comm_stream):
+                self.exchange()
+            self.kernel_stream.wait_stream(self.comm_stream)
+        self.match()

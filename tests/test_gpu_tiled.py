@@ -34,6 +34,21 @@ def test_strips_equal_whole_frame(ctx, w, h, block, search, world):
     np.testing.assert_array_equal(np.concatenate(costs).reshape(whole["cost"].shape).astype(np.uint32), whole["cost"])
 
 
+@pytest.mark.parametrize("w,h,block,search,world", [(640, 368, 16, 16, 2), (512, 288, 8, 32, 3)])
+def test_stream_strips_equal_whole_frames(ctx, w, h, block, search, world):
+    frames = synth.make_stream(4, w, h, search)
+    whole = ctx.block_match(frames[:-1], frames[1:], block, search, 0, want=("entries",))["entries"]
+    parts = []
+    for rank in range(world):
+        t = odist.TiledStreamMatcher(ctx, w, h, block, search, 0, len(frames), rank, world)
+        t.load(frames, fill_halos=True)
+        t.run(exchange=False)
+        ctx.sync()
+        parts.append(t.entries.cpu().numpy())
+    got = np.concatenate(parts, axis=1)
+    assert got.tobytes() == whole.tobytes()
+
+
 def _worker(rank, world, port, out_dir):
     import torch
     import torch.distributed as dist
@@ -49,9 +64,21 @@ def _worker(rank, world, port, out_dir):
         t.load(prev, cur)
         t.run()
         got = t.gather_entries()
+        # stream of tiled frames: one halo exchange for all frames, one batched strip launch
+        frames = synth.make_stream(3, 1920, 1088, 16)
+        ts = odist.TiledStreamMatcher(ctx, 1920, 1088, 16, 16, 0, 3, rank, world)
+        ts.load(frames)
+        ts.run()
+        ctx.sync()
+        mine = ts.entries.cpu().numpy()
+        ref = ctx.block_match(frames[:-1], frames[1:], 16, 16, 0, want=("entries",))["entries"]
+        s = ts.strip
+        stream_ok = mine.tobytes() == ref[:, s.by0 * ts.nbx:(s.by0 + s.nby) * ts.nbx].tobytes()
+        flags = torch.tensor([int(stream_ok)], device=f"cuda:{rank}")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         if rank == 0:
             whole = ctx.block_match(prev, cur, block, search, 0, want=("entries",))["entries"]
-            ok = got.tobytes() == whole.tobytes()
+            ok = got.tobytes() == whole.tobytes() and bool(flags.item())
             # detector on the gathered list == detector on the single-GPU list (same order, same bits)
             a = ctx.detect_block_motion(got)
             b = ctx.detect_block_motion(whole)

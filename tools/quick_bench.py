@@ -33,19 +33,10 @@ def run(ctx, w, h, block, search, n_pairs, iters=20, metric=0):
 if __name__ == "__main__":
     ctx = capi.Context(0)
     print(capi.version(), ctx.device_info())
-    for prune in (1, 0):
-        ctx.set_option("block_match_prune", prune)
-        ctx.set_option("block_match_stats", 1)
-        print("== prune", prune)
-        run(ctx, 1920, 1080, 16, 16, 1)
+    for chunk in (0, 4, 8, 16, 32, 64):
+        ctx.set_option("block_match_chunk_pairs", chunk)
+        print("== chunk", chunk)
         run(ctx, 1920, 1080, 16, 16, 64)
-        print(ctx.block_match_stats())
-        run(ctx, 640, 360, 16, 8, 64)
-        run(ctx, 3840, 2160, 8, 32, 8)
-        print(ctx.block_match_stats())
-        run(ctx, 3840, 2160, 16, 32, 8)
-        run(ctx, 1920, 1080, 8, 16, 16)
-        run(ctx, 1920, 1080, 8, 8, 16)
-        run(ctx, 7680, 4320, 16, 16, 4)
-        ctx.set_option("block_match_stats", 0)
-        run(ctx, 1920, 1080, 16, 16, 64)
+    ctx.set_option("block_match_chunk_pairs", 0)
+    run(ctx, 3840, 2160, 8, 32, 8)
+    run(ctx, 7680, 4320, 16, 16, 4)
