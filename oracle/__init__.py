@@ -24,7 +24,7 @@ def build(force: bool = False) -> str:
     """Compile the C restatement (gcc, see oracle/Makefile)."""
     src_newer = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-        for f in ("ofps_oracle.c", "ofps_oracle.h", "camera_almeida.inc", "Makefile")
+        for f in ("ofps_oracle.c", "cv_front.c", "ofps_oracle.h", "camera_almeida.inc", "Makefile")
     )
     if force or src_newer:
         subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []))
@@ -90,6 +90,17 @@ def _declare(L: C.CDLL) -> None:
                        C.POINTER(C.c_int16), C.POINTER(C.c_uint32), C.c_void_p, C.c_int]
         fn.restype = C.c_long
     L.orc_max_threads.restype = C.c_int
+    L.orc_bgr_to_gray.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+    L.orc_bgr_to_gray.restype = None
+    L.orc_bgr_to_rgba.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+    L.orc_bgr_to_rgba.restype = None
+    L.orc_mfield_size.argtypes = [C.c_size_t] * 6 + [szp, szp]
+    L.orc_mfield_size.restype = None
+    L.orc_contrast_mask.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.POINTER(C.c_int32)]
+    L.orc_contrast_mask.restype = None
+    L.orc_flow_entries.argtypes = [f32p, C.c_size_t, u8p, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                                   C.c_void_p, C.c_size_t]
+    L.orc_flow_entries.restype = C.c_size_t
 
 
 def _f32p(a):
@@ -265,3 +276,56 @@ def block_match(prev: np.ndarray, cur: np.ndarray, block: int, rng: int, metric:
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+# ------------------------------------------------------------------ cv-decoder dense-flow front end
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def bgr_to_gray(img: np.ndarray, rgb_order: bool = False) -> np.ndarray:
+    """cvtColor(COLOR_BGR2GRAY) (cv-decoder/src/lib.rs:138); img = u8[h,w,3|4]."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, ch = img.shape
+    gray = np.zeros((h, w), np.uint8)
+    lib().orc_bgr_to_gray(_u8p(img), w, h, w * ch, ch, int(rgb_order), _u8p(gray), w)
+    return gray
+
+
+def bgr_to_rgba(img: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, ch = img.shape
+    out = np.zeros((h, w, 4), np.uint8)
+    lib().orc_bgr_to_rgba(_u8p(img), w, h, w * ch, ch, _u8p(out))
+    return out
+
+
+def mfield_size(frame_w, frame_h, ar_x=1, ar_y=1, max_w=150, max_h=150):
+    dx, dy = C.c_size_t(0), C.c_size_t(0)
+    lib().orc_mfield_size(frame_w, frame_h, ar_x, ar_y, max_w, max_h, C.byref(dx), C.byref(dy))
+    return int(dx.value), int(dy.value)
+
+
+def contrast_mask(gray: np.ndarray, return_sobel: bool = False):
+    """Sobel(1,1,5) -> threshold 20 -> dilate 11x11 ellipse (cv-decoder/src/lib.rs:204-236); u8 0/255."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    mask = np.zeros((h, w), np.uint8)
+    sob = np.zeros((h, w), np.int32)
+    lib().orc_contrast_mask(_u8p(gray), w, h, w, _u8p(mask), sob.ctypes.data_as(C.POINTER(C.c_int32)))
+    return (mask, sob) if return_sobel else mask
+
+
+def flow_entries(flow: np.ndarray, mask=None, gw: int = 0, gh: int = 0) -> np.ndarray:
+    """Dense flow f32[h,w,2] (+ u8 mask[h,w]) -> MotionEntry f32[n,4] (cv-decoder/src/lib.rs:238-291)."""
+    flow = np.ascontiguousarray(flow, np.float32)
+    h, w, _ = flow.shape
+    cap = max(w * h, gw * gh, 1)
+    out = np.zeros((cap, 4), np.float32)
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, np.uint8)
+        mp = _u8p(mask)
+    else:
+        mp = None
+    n = lib().orc_flow_entries(_f32p(flow), 2 * w, mp, w, w, h, gw, gh, out.ctypes.data, cap)
+    return out[:n].copy()

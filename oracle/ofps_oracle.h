@@ -136,6 +136,25 @@ long orc_block_match_fast(const uint8_t *prev, const uint8_t *cur, int w, int h,
                           int16_t *mv_xy, uint32_t *cost, orc_mv *entries, int threads);
 int orc_max_threads(void);
 
+/* ------------------------------------------------- cv-decoder dense-flow front end (cv_front.c) */
+/* PINNED against OpenCV itself (cv2 4.13 run with the reference's call parameters;
+ * tests/golden/make_golden_cv.py -> tests/golden/golden_cv_v1.npz). */
+/* cvtColor(COLOR_BGR2GRAY) on 8-bit pixels (cv-decoder/src/lib.rs:138). */
+void orc_bgr_to_gray(const uint8_t *src, int w, int h, int stride, int channels, int rgb_order,
+                     uint8_t *gray, int gray_stride);
+/* out_frame: BGR(A) -> RGBA, a = 255 (cv-decoder/src/lib.rs:145-153; ofps/src/decoder.rs:19-26). */
+void orc_bgr_to_rgba(const uint8_t *src, int w, int h, int stride, int channels, uint8_t *rgba);
+/* motion-field size from frame size / aspect scale / max size (cv-decoder/src/lib.rs:90-118). */
+void orc_mfield_size(size_t frame_w, size_t frame_h, size_t ar_x, size_t ar_y, size_t max_w, size_t max_h,
+                     size_t *dx, size_t *dy);
+/* Sobel(1,1,k5) -> threshold(>20) -> dilate(11x11 ellipse), all BORDER_REFLECT_101
+ * (cv-decoder/src/lib.rs:204-236).  mask: w*h bytes 0/255; sobel_out optional (w*h int32). */
+void orc_contrast_mask(const uint8_t *gray, int w, int h, int stride, uint8_t *mask, int32_t *sobel_out);
+/* dense flow (+ optional mask) -> MotionEntry list, per pixel (gw == 0) or through the gw x gh
+ * down-sampling densifier, touched cells in BTreeSet<(x,y)> order (cv-decoder/src/lib.rs:238-291). */
+size_t orc_flow_entries(const float *flow, size_t flow_stride, const uint8_t *mask, size_t mask_stride, int w, int h,
+                        size_t gw, size_t gh, orc_mv *out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,3 +135,39 @@ def block_match(prev, cur, block, search, metric=0):
             sx, sy = x0 + block // 2 + dx, y0 + block // 2 + dy
             ent[by * nbx + bx] = (F(sx) * nx, F(sy) * ny, F(dx) * -nx, F(dy) * -ny)
     return mv, cost, ent
+
+
+# ---------------------------------------------------------------- cv-decoder dense-flow front end
+def mfield_size(frame_w, frame_h, ar_x, ar_y, max_w, max_h):
+    """cv-decoder/src/lib.rs:90-118 (usize arithmetic)."""
+    ratio = (frame_w * ar_x, frame_h * ar_y)
+    w, h = min(max_w, frame_w), min(max_h, frame_h)
+    width_based = (w, w * ratio[1] // ratio[0])
+    height_based = (h * ratio[0] // ratio[1], h)
+    return width_based if width_based[0] < height_based[0] else height_based
+
+
+def flow_entries(flow, mask=None, gw=0, gh=0):
+    """cv-decoder/src/lib.rs:238-291, literally: raster loop, optional mask test, per-pixel push or
+    down-sampling densifier + BTreeSet<(x,y)> of touched cells."""
+    h, w, _ = flow.shape
+    nx, ny = F(F(1) / F(w)), F(F(1) / F(h))
+    out = []
+    dens = Densifier(gw, gh) if gw else None
+    points = set()
+    for y in range(h):
+        for x in range(w):
+            if mask is not None and mask[y, x] < 0.1:
+                continue
+            pos = (F(F(F(x) + F(0.5)) * nx), F(F(F(y) + F(0.5)) * ny))
+            motion = (F(flow[y, x, 0] * nx), F(flow[y, x, 1] * ny))
+            if dens is not None:
+                points.add(dens.add_vector(pos[0], pos[1], motion[0], motion[1]))
+            else:
+                out.append((pos[0], pos[1], motion[0], motion[1]))
+    if dens is not None:
+        field = dens.field()
+        gx, gy = F(F(1) / F(gw)), F(F(1) / F(gh))
+        for (x, y) in sorted(points):
+            out.append((F(F(F(x) + F(0.5)) * gx), F(F(F(y) + F(0.5)) * gy), field[y, x, 0], field[y, x, 1]))
+    return np.array(out, np.float32).reshape(-1, 4)
