@@ -44,9 +44,13 @@ WORKLOAD = "1080p block matching 16x16/+-16 SAD, 65-frame synthetic stream = 64 
 # algorithmic traffic per frame pair: two u8 planes read once + 16 B per block out
 BYTES_PER_PAIR = 2 * W * H + 16 * NBLOCKS
 ABSDIFF_PER_PAIR = NBLOCKS * (2 * SEARCH + 1) ** 2 * BLOCK * BLOCK
-# ncu --set full capture of block_match_tile_kernel (profiles/): dram bytes read+write per launch
-# measured: 35.25 MB for a 17-frame capture = every frame read exactly once, writes stay in L2 (profiles/r1_block_match_ncu.md)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = (PAIRS + 1) * W * H
+# ncu --set full captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum per step of 64 pairs.
+#  * pruned path (the default, what `value` times): window_sum 148.8+206.6 MB, prune 397.6+11.1 MB, work list
+#    135.6+5.0 MB = 904.7 MB (profiles/r1_pruned_path_ncu.md) — 3.3x the algorithmic bytes: the u16 window-sum plane
+#    is written and re-read through HBM and each of the three kernels reads the frames once;
+#  * exhaustive kernel: every frame read exactly once, entries written (profiles/r1_block_match_ncu.md).
+NCU_TRAFFIC_BYTES_PRUNED_STEP = 904_700_000
+NCU_TRAFFIC_BYTES_EXHAUSTIVE_STEP = (PAIRS + 1) * W * H + PAIRS * NBLOCKS * 16
 
 
 def _peaks():
@@ -261,7 +265,7 @@ def run_ours(args):
                     "api": "ofpsb_block_match_batch (pinned host frames -> MotionEntry lists)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PRUNED_STEP, "peak_source": peak_src,
                          "kernel": "hot-path pass = window_sum_kernel<16> + prune_kernel<16,16> + block_match_list_kernel<16,16,17,4,288,SAD> "
                                    "(per-kernel shares: profiles/)",
                          "bytes_per_launch": BYTES_PER_PAIR * PAIRS, "kernel_ms": step_s * 1e3,
@@ -271,7 +275,8 @@ def run_ours(args):
                            "ms_per_step": exh_ms / args.steps, "gpu_launches": int(exh_launches),
                            "kernel": "block_match_tma_kernel<16,16,17,4,288,SAD> (every candidate of every block)",
                            "hbm": {"achieved": BYTES_PER_PAIR * PAIRS / exh_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                   "frac": BYTES_PER_PAIR * PAIRS / exh_s / 1e9 / hbm_peak},
+                                   "frac": BYTES_PER_PAIR * PAIRS / exh_s / 1e9 / hbm_peak,
+                                   "traffic": NCU_TRAFFIC_BYTES_EXHAUSTIVE_STEP},
                            "alu": {"bound": "int-alu (VABSDIFF4.U8.ACC 64 lanes/clk/SM; exhaustive SAD is ~540 abs-diff/byte)",
                                    "achieved": alu_ach, "peak": alu_peak, "unit": "T absdiff/s", "frac": alu_ach / alu_peak}},
             "clocks": clocks,

@@ -154,6 +154,15 @@ int ofpsb_densify(ofpsb_ctx *ctx, const ofps_mv *entries, size_t n, size_t gw, s
 int ofpsb_densify_dev(ofpsb_ctx *ctx, const ofps_mv *d_entries, size_t n, size_t gw, size_t gh,
                       float *d_field_xy, float *d_counts);
 
+/* The flow-extract dense pipeline (flow-extract/src/main.rs:72-83): densify into a w x h field (GPU, bit-exact
+ * order), MotionFieldDensifier::interpolate_empty_cells (ofps/src/motion_field.rs:193-294), sum ./ counts.
+ * The hole fill is strictly sequential by definition (ordered set keyed by the changing neighbour counts) and
+ * runs on the host, as in the reference; see csrc/hole_fill.cu.  field_xy: w*h*2 floats. */
+int ofpsb_flow_field(ofpsb_ctx *ctx, const ofps_mv *entries, size_t n, size_t w, size_t h, float *field_xy);
+/* The hole fill alone, in place on a densifier state (sums and counts, 2*w*h floats each).  Host arithmetic
+ * only: needs no context and no device. */
+int ofpsb_interpolate_empty_cells(float *sums_xy, float *counts_xy, size_t w, size_t h);
+
 /* --------------------------------------------------------------- detector
  * BlockMotionDetection::detect_motion.  *has_motion = 1 for Some, 0 for None; *area =
  * cell count of the winning island (0 when None); *dim = block_dim; field_xy receives
@@ -192,6 +201,53 @@ int ofpsb_frame_detect(ofpsb_ctx *ctx, const uint8_t *prev, const uint8_t *cur, 
                        float min_size, size_t subdivide, float target_motion,
                        ofps_mv *entries, size_t *n_blocks,
                        int *has_motion, size_t *area, size_t *dim, float *field_xy, size_t field_cap_cells);
+
+/* ------------------------------------------- cv-decoder dense-flow front end
+ * What CvDecoder::process_frame does around the third-party optical-flow call
+ * (cv-decoder/src/lib.rs:84-291); the flow itself (OpenCV Farneback / RLOF) is an input.
+ *
+ * ofpsb_mfield_size: motion-field size from the frame size, the aspect-ratio scale and the
+ * "Width" / "Height" properties (cv-decoder/src/lib.rs:90-118).  Host arithmetic only. */
+int ofpsb_mfield_size(size_t frame_w, size_t frame_h, size_t ar_x, size_t ar_y, size_t max_w, size_t max_h,
+                      size_t *dx, size_t *dy);
+/* cvtColor(frame, COLOR_BGR2GRAY) (cv-decoder/src/lib.rs:138; OpenCV 4 fixed point, bit-exact) and the
+ * RGBA out_frame (:145-153).  src: u8, `channels` = 3 or 4 interleaved, `stride` bytes per row;
+ * rgb_order != 0 reads R,G,B instead of B,G,R.  gray: w*h bytes, rgba: w*h*4 bytes; either may be NULL. */
+int ofpsb_frame_convert(ofpsb_ctx *ctx, const uint8_t *src, int w, int h, int stride, int channels, int rgb_order,
+                        uint8_t *gray, uint8_t *rgba);
+int ofpsb_frame_convert_dev(ofpsb_ctx *ctx, const uint8_t *d_src, int w, int h, int stride, int channels,
+                            int rgb_order, uint8_t *d_gray, int gray_stride, uint8_t *d_rgba);
+/* imgproc::resize(frame, (dw, dh), INTER_LINEAR) on the 8-bit frame, the "Process Fullres" = off path
+ * (cv-decoder/src/lib.rs:127-135): OpenCV's fixed-point bilinear arithmetic, bit-exact.  Reductions only
+ * (dw <= sw, dh <= sh — the reference never enlarges; OFPSB_E_INVALID otherwise).  dst: dw*dh*channels bytes. */
+int ofpsb_frame_resize(ofpsb_ctx *ctx, const uint8_t *src, int sw, int sh, int stride, int channels,
+                       uint8_t *dst, int dw, int dh);
+int ofpsb_frame_resize_dev(ofpsb_ctx *ctx, const uint8_t *d_src, int sw, int sh, int stride, int channels,
+                           uint8_t *d_dst, int dw, int dh, int dst_stride);
+/* Contrast mask of the Farneback path (cv-decoder/src/lib.rs:204-236): Sobel(CV_32F, 1, 1, ksize 5) ->
+ * threshold(20, 255, BINARY) -> dilate(11x11 MORPH_ELLIPSE), all with BORDER_REFLECT_101, fused in one
+ * kernel.  mask: w*h bytes, 255 where the reference's f32 mask is 255, else 0 (bit-exact with OpenCV). */
+int ofpsb_contrast_mask(ofpsb_ctx *ctx, const uint8_t *gray, int w, int h, int stride, uint8_t *mask);
+int ofpsb_contrast_mask_dev(ofpsb_ctx *ctx, const uint8_t *d_gray, int w, int h, int stride,
+                            uint8_t *d_mask, int mask_stride);
+/* Dense flow image -> MotionEntry list (cv-decoder/src/lib.rs:238-291).  flow: h rows of w (fx,fy) f32
+ * pairs in pixels; mask (optional, w*h bytes): pixels with mask == 0 are skipped (the RLOF path passes
+ * NULL).  gw == gh == 0 ("Process Fullres" off): one entry per kept pixel in raster order, pos =
+ * (x+0.5, y+0.5) .* (1/w, 1/h), motion = flow .* (1/w, 1/h).  Otherwise the kept pixels go through a
+ * gw x gh MotionFieldDensifier and one entry per touched cell comes out in (x, y) lexicographic order
+ * (the reference's BTreeSet), pos = cell centre, motion = cell mean; sums follow the reference's raster
+ * order in un-fused f32 (bit-exact).  *n receives the entry count; OFPSB_E_CAPACITY if it exceeds cap
+ * (the first cap entries are still written). */
+int ofpsb_flow_entries(ofpsb_ctx *ctx, const float *flow_xy, const uint8_t *mask, int w, int h,
+                       size_t gw, size_t gh, ofps_mv *entries, size_t cap, size_t *n);
+/* Device variant: strides in elements (floats / bytes); d_entries device memory; *n returned to host. */
+int ofpsb_flow_entries_dev(ofpsb_ctx *ctx, const float *d_flow_xy, size_t flow_stride, const uint8_t *d_mask,
+                           size_t mask_stride, int w, int h, size_t gw, size_t gh,
+                           ofps_mv *d_entries, size_t cap, size_t *n);
+/* The whole post-flow stage of one frame in one call: gray (+ flow) in, entries out; mask and cell sums
+ * stay in HBM.  use_mask = 1 for the Farneback path, 0 for RLOF. */
+int ofpsb_cv_flow_frame(ofpsb_ctx *ctx, const uint8_t *gray, int gray_stride, const float *flow_xy, int w, int h,
+                        int use_mask, size_t gw, size_t gh, ofps_mv *entries, size_t cap, size_t *n);
 
 /* ------------------------------------------------------ interchange files
  * .mvec: per frame u32 LE count, then count x 4 f32 LE (motion-extract/src/main.rs:23-35). */

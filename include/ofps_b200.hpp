@@ -259,6 +259,96 @@ private:
     int have_ = 0;
 };
 
+// ---- Decoder: the reference's cv-decoder (cv-decoder/src/lib.rs:17-307) with its two third-party calls
+// abstracted — the frame source (cv::VideoCapture::read) and the optical flow (cv::calcOpticalFlowFarneback /
+// cv::optflow::calcOpticalFlowDenseRLOF) are callbacks of the host; everything the reference does AROUND them
+// runs on the GPU: resize (:127-135), BGR2GRAY (:138), RGBA out_frame (:145-153), the Sobel / threshold /
+// dilate contrast mask (:204-236) and the flow -> MotionEntry conversion through the down-sampling
+// MotionFieldDensifier (:238-291).  Same property names and bounds as the reference (:34-52).
+class DenseFlowDecoder {
+public:
+    std::pair<size_t, size_t> max_mfield_size{150, 150};   // "Width", "Height"
+    bool use_rlof = false;                                 // "RLOF": no contrast mask
+    bool process_fullres = true;                           // "Process Fullres"
+
+    // Fills `bgr` (h rows of w interleaved B,G,R bytes) and the size; false at end of stream.
+    using FrameSource = std::function<bool(std::vector<uint8_t>& bgr, int& w, int& h)>;
+    // Dense flow from the previous to the current frame into flow_xy (w*h*2 f32, pixels).  `initial` is true
+    // when flow_xy still holds the previous result (OPTFLOW_USE_INITIAL_FLOW, cv-decoder:160-164).
+    using FlowSource = std::function<void(const uint8_t* old_gray, const uint8_t* gray, const uint8_t* old_bgr,
+                                          const uint8_t* bgr, int w, int h, bool rlof, bool initial, float* flow_xy)>;
+
+    DenseFlowDecoder(std::shared_ptr<Context> ctx, FrameSource frames, FlowSource flow, double framerate = 0.0,
+                     std::pair<size_t, size_t> aspect_ratio_scale = {1, 1})
+        : ctx_(std::move(ctx)), frames_(std::move(frames)), flow_fn_(std::move(flow)), fps_(framerate), ar_(aspect_ratio_scale)
+    {
+    }
+
+    PropList props_mut()
+    {
+        return {{"Width", UsizeProp{&max_mfield_size.first, 1, 2000}},
+                {"Height", UsizeProp{&max_mfield_size.second, 1, 2000}},
+                {"RLOF", BoolProp{&use_rlof}},
+                {"Process Fullres", BoolProp{&process_fullres}}};
+    }
+    std::optional<double> get_framerate() const { return fps_ > 0 ? std::optional<double>(fps_) : std::nullopt; }
+    std::optional<std::pair<size_t, size_t>> get_aspect() const { return std::make_pair((size_t)gw_, (size_t)gh_); }
+
+    bool process_frame(MotionVectors& field, std::vector<RGBA>* out_frame, size_t* out_height, size_t skip_frames)
+    {
+        size_t dx = 0, dy = 0;
+        for (size_t cnt = 0; cnt <= skip_frames; cnt++) {
+            int w = 0, h = 0;
+            if (!frames_(tmp_, w, h)) throw Error(OFPSB_E_IO, "Failed to grab frame");
+            old_frame_.swap(frame_);
+            old_gray_.swap(gray_);
+            ogw_ = gw_;
+            ogh_ = gh_;
+            check(ofpsb_mfield_size((size_t)w, (size_t)h, ar_.first, ar_.second, max_mfield_size.first, max_mfield_size.second,
+                                    &dx, &dy));
+            if (process_fullres) {
+                frame_.swap(tmp_);
+                gw_ = w;
+                gh_ = h;
+            } else {
+                frame_.resize(dx * dy * 3);
+                check(ofpsb_frame_resize(ctx_->get(), tmp_.data(), w, h, w * 3, 3, frame_.data(), (int)dx, (int)dy));
+                gw_ = (int)dx;
+                gh_ = (int)dy;
+            }
+            gray_.resize((size_t)gw_ * gh_);
+            const bool want_rgba = out_frame && cnt == skip_frames;
+            if (want_rgba) out_frame->resize((size_t)gw_ * gh_);
+            check(ofpsb_frame_convert(ctx_->get(), frame_.data(), gw_, gh_, gw_ * 3, 3, 0, gray_.data(),
+                                      want_rgba ? reinterpret_cast<uint8_t*>(out_frame->data()) : nullptr));
+        }
+        if (out_frame && out_height) *out_height = (size_t)gh_;
+        if (gw_ != ogw_ || gh_ != ogh_) return false;   // first frame / size change (cv-decoder:155-157)
+        const size_t npix = (size_t)gw_ * gh_;
+        const bool initial = flow_.size() == 2 * npix;
+        flow_.resize(2 * npix);
+        flow_fn_(old_gray_.data(), gray_.data(), old_frame_.data(), frame_.data(), gw_, gh_, use_rlof, initial, flow_.data());
+        const size_t cap = process_fullres ? dx * dy : npix;
+        scratch_.resize(cap ? cap : 1);
+        size_t n = 0;
+        check(ofpsb_cv_flow_frame(ctx_->get(), gray_.data(), gw_, flow_.data(), gw_, gh_, use_rlof ? 0 : 1,
+                                  process_fullres ? dx : 0, process_fullres ? dy : 0, scratch_.data(), cap, &n));
+        field.insert(field.end(), scratch_.begin(), scratch_.begin() + (std::ptrdiff_t)n);
+        return true;
+    }
+
+private:
+    std::shared_ptr<Context> ctx_;
+    FrameSource frames_;
+    FlowSource flow_fn_;
+    double fps_;
+    std::pair<size_t, size_t> ar_;
+    std::vector<uint8_t> tmp_, frame_, old_frame_, gray_, old_gray_;
+    std::vector<float> flow_;
+    MotionVectors scratch_;
+    int gw_ = 0, gh_ = 0, ogw_ = 0, ogh_ = 0;
+};
+
 }  // namespace ofps_b200
 
 #endif  // OFPS_B200_HPP

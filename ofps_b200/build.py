@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libofps_b200.so")
-SOURCES = ["api.cu", "block_match.cu", "block_match_tma.cu", "block_match_prune.cu", "densify.cu", "detect.cu", "almeida.cu"]
+SOURCES = ["api.cu", "block_match.cu", "block_match_tma.cu", "block_match_prune.cu", "densify.cu", "detect.cu", "almeida.cu", "cv_front.cu", "hole_fill.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "block_match_common.cuh"), os.path.join(HERE, "..", "include", "ofps_b200.h")]
 
 NVCC_FLAGS = [

@@ -59,6 +59,8 @@ SIGNATURES = {
                                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "ofpsb_densify": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp]),
     "ofpsb_densify_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp]),
+    "ofpsb_flow_field": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp]),
+    "ofpsb_interpolate_empty_cells": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t]),
     "ofpsb_block_dim": (C.c_int, [C.c_float, C.c_size_t, _szp]),
     "ofpsb_detect_block_motion": (C.c_int, [_vp, _vp, C.c_size_t, C.c_float, C.c_size_t, C.c_float, _intp, _szp,
                                             _szp, _vp, C.c_size_t]),
@@ -70,6 +72,18 @@ SIGNATURES = {
                                     C.c_size_t, C.c_uint64, _f32p]),
     "ofpsb_frame_detect": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_float, C.c_size_t, C.c_float, _vp, _szp, _intp, _szp, _szp, _vp, C.c_size_t]),
+    "ofpsb_mfield_size": (C.c_int, [C.c_size_t] * 6 + [_szp, _szp]),
+    "ofpsb_frame_convert": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "ofpsb_frame_convert_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp]),
+    "ofpsb_frame_resize": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int]),
+    "ofpsb_frame_resize_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int]),
+    "ofpsb_contrast_mask": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "ofpsb_contrast_mask_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int]),
+    "ofpsb_flow_entries": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_size_t, C.c_size_t, _vp, C.c_size_t, _szp]),
+    "ofpsb_flow_entries_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                                         _vp, C.c_size_t, _szp]),
+    "ofpsb_cv_flow_frame": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, _vp,
+                                      C.c_size_t, _szp]),
     "ofpsb_mvec_append": (C.c_int, [C.c_char_p, _vp, C.c_size_t, C.c_int]),
     "ofpsb_mvec_read": (C.c_int, [C.c_char_p, C.c_size_t, _vp, C.c_size_t, _szp]),
     "ofpsb_flo_write": (C.c_int, [C.c_char_p, _vp, C.c_size_t, C.c_size_t]),
@@ -292,6 +306,13 @@ class Context:
     def densify_dev(self, d_entries, n: int, gw: int, gh: int, d_field, d_counts=None):
         check(lib().ofpsb_densify_dev(self._h, _ptr(d_entries), n, gw, gh, _ptr(d_field), _ptr(d_counts)))
 
+    def flow_field(self, entries, w: int, h: int) -> np.ndarray:
+        """flow-extract's dense field: densify (GPU) -> interpolate_empty_cells (host, sequential) -> mean."""
+        mv = as_mv(entries)
+        field = np.empty((h, w, 2), np.float32)
+        check(lib().ofpsb_flow_field(self._h, mv.ctypes.data, len(mv), w, h, field.ctypes.data))
+        return field
+
     def detect_block_motion(self, entries, min_size: float = 0.05, subdivide: int = 3, target_motion: float = 0.003,
                             d_entries=None, n: int | None = None):
         """Returns (has_motion, area, dim, field[dim,dim,2]).  Pass ``d_entries``/``n`` for device-resident input."""
@@ -338,6 +359,84 @@ class Context:
             check(lib().ofpsb_almeida(self._h, mv.ctypes.data, len(mv), aspect, fov_y_deg, int(use_ransac), num_iters,
                                       inlier_angle_deg, ransac_samples, seed, qp))
         return q
+
+
+    # ---- cv-decoder dense-flow front end
+    def frame_convert(self, img: np.ndarray, rgb_order: bool = False, want_gray: bool = True, want_rgba: bool = False):
+        """u8[h,w,3|4] BGR(A) -> (gray u8[h,w] | None, rgba u8[h,w,4] | None)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, ch = img.shape
+        gray = np.empty((h, w), np.uint8) if want_gray else None
+        rgba = np.empty((h, w, 4), np.uint8) if want_rgba else None
+        check(lib().ofpsb_frame_convert(self._h, img.ctypes.data, w, h, w * ch, ch, int(rgb_order), _ptr(gray), _ptr(rgba)))
+        return gray, rgba
+
+    def frame_convert_dev(self, d_src, w: int, h: int, stride: int, channels: int, rgb_order: bool, d_gray, gray_stride: int,
+                          d_rgba=None):
+        check(lib().ofpsb_frame_convert_dev(self._h, _ptr(d_src), w, h, stride, channels, int(rgb_order), _ptr(d_gray),
+                                            gray_stride, _ptr(d_rgba)))
+
+    def frame_resize(self, img: np.ndarray, dw: int, dh: int) -> np.ndarray:
+        """resize(INTER_LINEAR) of u8[h,w,3|4] to (dh, dw) (reductions only)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, ch = img.shape
+        out = np.empty((dh, dw, ch), np.uint8)
+        check(lib().ofpsb_frame_resize(self._h, img.ctypes.data, w, h, w * ch, ch, out.ctypes.data, dw, dh))
+        return out
+
+    def contrast_mask(self, gray: np.ndarray) -> np.ndarray:
+        gray = np.ascontiguousarray(gray, np.uint8)
+        h, w = gray.shape
+        mask = np.empty((h, w), np.uint8)
+        check(lib().ofpsb_contrast_mask(self._h, gray.ctypes.data, w, h, w, mask.ctypes.data))
+        return mask
+
+    def contrast_mask_dev(self, d_gray, w: int, h: int, stride: int, d_mask, mask_stride: int):
+        check(lib().ofpsb_contrast_mask_dev(self._h, _ptr(d_gray), w, h, stride, _ptr(d_mask), mask_stride))
+
+    def flow_entries(self, flow: np.ndarray, mask=None, gw: int = 0, gh: int = 0, cap: int | None = None) -> np.ndarray:
+        """Dense flow f32[h,w,2] (+ u8 mask[h,w]) -> MotionEntry f32[n,4]."""
+        flow = np.ascontiguousarray(flow, np.float32)
+        h, w, _ = flow.shape
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+        cap = (gw * gh if gw else w * h) if cap is None else cap
+        out = np.empty((max(cap, 1), 4), np.float32)
+        n = C.c_size_t()
+        check(lib().ofpsb_flow_entries(self._h, flow.ctypes.data, _ptr(mask), w, h, gw, gh, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def flow_entries_dev(self, d_flow, flow_stride: int, d_mask, mask_stride: int, w: int, h: int, gw: int, gh: int,
+                         d_entries, cap: int) -> int:
+        n = C.c_size_t()
+        check(lib().ofpsb_flow_entries_dev(self._h, _ptr(d_flow), flow_stride, _ptr(d_mask), mask_stride, w, h, gw, gh,
+                                           _ptr(d_entries), cap, C.byref(n)))
+        return int(n.value)
+
+    def cv_flow_frame(self, gray, flow: np.ndarray, use_mask: bool = True, gw: int = 0, gh: int = 0) -> np.ndarray:
+        """gray u8[h,w] + flow f32[h,w,2] -> MotionEntry f32[n,4]: mask, densifier and ordering on the GPU."""
+        flow = np.ascontiguousarray(flow, np.float32)
+        h, w, _ = flow.shape
+        gray = np.ascontiguousarray(gray, np.uint8) if gray is not None else None
+        cap = gw * gh if gw else w * h
+        out = np.empty((max(cap, 1), 4), np.float32)
+        n = C.c_size_t()
+        check(lib().ofpsb_cv_flow_frame(self._h, _ptr(gray), w, flow.ctypes.data, w, h, int(use_mask), gw, gh,
+                                        out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].copy()
+
+
+def mfield_size(frame_w: int, frame_h: int, ar_x: int = 1, ar_y: int = 1, max_w: int = 150, max_h: int = 150):
+    dx, dy = C.c_size_t(), C.c_size_t()
+    check(lib().ofpsb_mfield_size(frame_w, frame_h, ar_x, ar_y, max_w, max_h, C.byref(dx), C.byref(dy)))
+    return int(dx.value), int(dy.value)
+
+
+def interpolate_empty_cells(sums: np.ndarray, counts: np.ndarray):
+    """In place on a densifier state, sums / counts f32[h,w,2] (host arithmetic, no device)."""
+    assert sums.dtype == np.float32 and counts.dtype == np.float32 and sums.flags.c_contiguous and counts.flags.c_contiguous
+    h, w = sums.shape[:2]
+    check(lib().ofpsb_interpolate_empty_cells(sums.ctypes.data, counts.ctypes.data, w, h))
 
 
 def block_dim(min_size: float, subdivide: int) -> int:

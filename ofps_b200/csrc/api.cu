@@ -289,7 +289,8 @@ void ofpsb_destroy(ofpsb_ctx* ctx)
                       &ctx->d_counts, &ctx->d_misc, &ctx->d_detect_scratch, &ctx->densify.keys_a, &ctx->densify.keys_b,
                       &ctx->densify.vals_a, &ctx->densify.vals_b, &ctx->densify.hist, &ctx->densify.cell_start,
                       &ctx->densify.sums, &ctx->bm_scratch.sums, &ctx->bm_scratch.worklist, &ctx->almeida.state, &ctx->almeida.partial, &ctx->almeida.hyp,
-                      &ctx->almeida.inlier_idx, &ctx->almeida.flags};
+                      &ctx->almeida.inlier_idx, &ctx->almeida.flags, &ctx->flow.bounds, &ctx->flow.cells, &ctx->flow.tiles,
+                      &ctx->d_cv_src, &ctx->d_cv_small, &ctx->d_cv_gray, &ctx->d_cv_rgba, &ctx->d_cv_mask, &ctx->d_cv_flow, &ctx->d_cv_count};
     for (DevBuf* b : bufs) b->release();
     ctx->h_misc.release();
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
@@ -620,6 +621,40 @@ int ofpsb_densify(ofpsb_ctx* ctx, const ofps_mv* entries, size_t n, size_t gw, s
     return OFPSB_OK;
 }
 
+int ofpsb_interpolate_empty_cells(float* sums_xy, float* counts_xy, size_t w, size_t h)
+{
+    if (!sums_xy || !counts_xy || w == 0 || h == 0 || w > (1u << 24) || h > (1u << 24)) {
+        set_error("interpolate_empty_cells: invalid arguments");
+        return OFPSB_E_INVALID;
+    }
+    interpolate_empty_cells_host(sums_xy, counts_xy, w, h);
+    return OFPSB_OK;
+}
+
+int ofpsb_flow_field(ofpsb_ctx* ctx, const ofps_mv* entries, size_t n, size_t w, size_t h, float* field_xy)
+{
+    OFPSB_ENTER(ctx);
+    if (!field_xy || (n && !entries) || w == 0 || h == 0 || w > (1u << 24) || h > (1u << 24)) {
+        set_error("flow_field: invalid arguments (%zux%zu)", w, h);
+        return OFPSB_E_INVALID;
+    }
+    const size_t cells = w * h;
+    if (int rc = ctx->d_entries.reserve(n * sizeof(ofps_mv))) return rc;
+    if (int rc = ctx->d_field.reserve(cells * 8)) return rc;
+    if (int rc = ctx->d_counts.reserve(cells * 8)) return rc;
+    if (n) OFPSB_CUDA_TRY(cudaMemcpyAsync(ctx->d_entries.ptr, entries, n * sizeof(ofps_mv), cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = launch_densify(ctx->d_entries.as<ofps_mv>(), n, w, h, ctx->d_field.as<float>(), ctx->d_counts.as<float>(),
+                                ctx->densify, ctx->stream, &ctx->launches, ctx->opt_densify_path, /*raw=*/1))
+        return rc;
+    std::vector<float> counts(2 * cells);
+    OFPSB_CUDA_TRY(cudaMemcpyAsync(field_xy, ctx->d_field.ptr, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    OFPSB_CUDA_TRY(cudaMemcpyAsync(counts.data(), ctx->d_counts.ptr, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    OFPSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    interpolate_empty_cells_host(field_xy, counts.data(), w, h);
+    for (size_t i = 0; i < 2 * cells; i++) field_xy[i] = field_xy[i] / counts[i];   // MotionField::from (:297-308)
+    return OFPSB_OK;
+}
+
 // ------------------------------------------------------------------------------------ detector
 int ofpsb_block_dim(float min_size, size_t subdivide, size_t* dim)
 {
@@ -723,6 +758,233 @@ int ofpsb_frame_detect(ofpsb_ctx* ctx, const uint8_t* prev, const uint8_t* cur, 
         OFPSB_CUDA_TRY(cudaMemcpyAsync(entries, ctx->d_entries.ptr, nb * sizeof(ofps_mv), cudaMemcpyDeviceToHost, ctx->stream));
     return detect_from_device_entries(ctx, ctx->d_entries.as<ofps_mv>(), nb, min_size, subdivide, target_motion,
                                       has_motion, area, dim, field_xy, field_cap_cells);
+}
+
+// ------------------------------------------------------------- cv-decoder dense-flow front end
+int ofpsb_mfield_size(size_t frame_w, size_t frame_h, size_t ar_x, size_t ar_y, size_t max_w, size_t max_h, size_t* dx,
+                      size_t* dy)
+{
+    if (!dx || !dy || frame_w == 0 || frame_h == 0 || ar_x == 0 || ar_y == 0) {
+        set_error("mfield_size: invalid arguments");
+        return OFPSB_E_INVALID;
+    }
+    // cv-decoder/src/lib.rs:90-118 (usize arithmetic, truncating division)
+    const size_t r0 = frame_w * ar_x, r1 = frame_h * ar_y;
+    const size_t w = max_w < frame_w ? max_w : frame_w, h = max_h < frame_h ? max_h : frame_h;
+    const size_t wb1 = w * r1 / r0, hb0 = h * r0 / r1;
+    if (w < hb0) {
+        *dx = w;
+        *dy = wb1;
+    } else {
+        *dx = hb0;
+        *dy = h;
+    }
+    return OFPSB_OK;
+}
+
+int ofpsb_frame_convert_dev(ofpsb_ctx* ctx, const uint8_t* d_src, int w, int h, int stride, int channels, int rgb_order,
+                            uint8_t* d_gray, int gray_stride, uint8_t* d_rgba)
+{
+    OFPSB_ENTER(ctx);
+    if (!d_src) {
+        set_error("frame_convert: null source");
+        return OFPSB_E_INVALID;
+    }
+    return launch_frame_convert(d_src, w, h, stride, channels, rgb_order, d_gray, gray_stride, d_rgba, ctx->stream,
+                                &ctx->launches);
+}
+
+int ofpsb_frame_convert(ofpsb_ctx* ctx, const uint8_t* src, int w, int h, int stride, int channels, int rgb_order,
+                        uint8_t* gray, uint8_t* rgba)
+{
+    OFPSB_ENTER(ctx);
+    if (!src || w <= 0 || h <= 0 || (channels != 3 && channels != 4) || stride < w * channels) {
+        set_error("frame_convert: invalid arguments (w=%d h=%d stride=%d channels=%d)", w, h, stride, channels);
+        return OFPSB_E_INVALID;
+    }
+    const size_t npix = (size_t)w * h;
+    const int gstride = (w + 3) & ~3;
+    if (int rc = ctx->d_cv_src.reserve((size_t)stride * h)) return rc;
+    if (gray) if (int rc = ctx->d_cv_gray.reserve((size_t)gstride * h)) return rc;
+    if (rgba) if (int rc = ctx->d_cv_rgba.reserve(npix * 4)) return rc;
+    OFPSB_CUDA_TRY(cudaMemcpyAsync(ctx->d_cv_src.ptr, src, (size_t)stride * h, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = launch_frame_convert(ctx->d_cv_src.as<uint8_t>(), w, h, stride, channels, rgb_order,
+                                      gray ? ctx->d_cv_gray.as<uint8_t>() : nullptr, gstride,
+                                      rgba ? ctx->d_cv_rgba.as<uint8_t>() : nullptr, ctx->stream, &ctx->launches))
+        return rc;
+    if (gray)
+        OFPSB_CUDA_TRY(cudaMemcpy2DAsync(gray, (size_t)w, ctx->d_cv_gray.ptr, (size_t)gstride, (size_t)w, (size_t)h,
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+    if (rgba) OFPSB_CUDA_TRY(cudaMemcpyAsync(rgba, ctx->d_cv_rgba.ptr, npix * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    OFPSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return OFPSB_OK;
+}
+
+int ofpsb_frame_resize_dev(ofpsb_ctx* ctx, const uint8_t* d_src, int sw, int sh, int stride, int channels, uint8_t* d_dst,
+                           int dw, int dh, int dst_stride)
+{
+    OFPSB_ENTER(ctx);
+    if (!d_src || !d_dst) {
+        set_error("frame_resize: null pointer");
+        return OFPSB_E_INVALID;
+    }
+    return launch_frame_resize(d_src, sw, sh, stride, channels, d_dst, dw, dh, dst_stride, ctx->stream, &ctx->launches);
+}
+
+int ofpsb_frame_resize(ofpsb_ctx* ctx, const uint8_t* src, int sw, int sh, int stride, int channels, uint8_t* dst, int dw,
+                       int dh)
+{
+    OFPSB_ENTER(ctx);
+    if (!src || !dst || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || (channels != 3 && channels != 4) ||
+        stride < sw * channels) {
+        set_error("frame_resize: invalid arguments (%dx%d -> %dx%d, channels=%d)", sw, sh, dw, dh, channels);
+        return OFPSB_E_INVALID;
+    }
+    const size_t out_bytes = (size_t)dw * dh * channels;
+    if (int rc = ctx->d_cv_src.reserve((size_t)stride * sh)) return rc;
+    if (int rc = ctx->d_cv_small.reserve(out_bytes)) return rc;
+    OFPSB_CUDA_TRY(cudaMemcpyAsync(ctx->d_cv_src.ptr, src, (size_t)stride * sh, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = launch_frame_resize(ctx->d_cv_src.as<uint8_t>(), sw, sh, stride, channels, ctx->d_cv_small.as<uint8_t>(), dw,
+                                     dh, dw * channels, ctx->stream, &ctx->launches))
+        return rc;
+    OFPSB_CUDA_TRY(cudaMemcpyAsync(dst, ctx->d_cv_small.ptr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    OFPSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return OFPSB_OK;
+}
+
+int ofpsb_contrast_mask_dev(ofpsb_ctx* ctx, const uint8_t* d_gray, int w, int h, int stride, uint8_t* d_mask,
+                            int mask_stride)
+{
+    OFPSB_ENTER(ctx);
+    if (!d_gray || !d_mask) {
+        set_error("contrast_mask: null pointer");
+        return OFPSB_E_INVALID;
+    }
+    return launch_contrast_mask(d_gray, w, h, stride, d_mask, mask_stride, ctx->stream, &ctx->launches);
+}
+
+namespace {
+// gray (host, `stride` bytes per row) -> device plane with 16-byte aligned rows; returns its pitch
+int upload_gray(ofpsb_ctx* ctx, const uint8_t* gray, int w, int h, int stride, int* pitch)
+{
+    const int gp = (w + 15) & ~15;
+    if (int rc = ctx->d_cv_gray.reserve((size_t)gp * h)) return rc;
+    OFPSB_CUDA_TRY(cudaMemcpy2DAsync(ctx->d_cv_gray.ptr, (size_t)gp, gray, (size_t)stride, (size_t)w, (size_t)h,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    *pitch = gp;
+    return OFPSB_OK;
+}
+
+// count -> host, then the first min(count, cap) entries
+int fetch_entries(ofpsb_ctx* ctx, const ofps_mv* d_entries, ofps_mv* entries, size_t cap, size_t* n, const char* what)
+{
+    if (int rc = ctx->h_misc.reserve(256)) return rc;
+    OFPSB_CUDA_TRY(cudaMemcpyAsync(ctx->h_misc.ptr, ctx->d_cv_count.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    OFPSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const size_t cnt = (size_t)*ctx->h_misc.as<unsigned long long>();
+    if (n) *n = cnt;
+    const size_t take = cnt < cap ? cnt : cap;
+    if (entries && take) {
+        OFPSB_CUDA_TRY(cudaMemcpyAsync(entries, d_entries, take * sizeof(ofps_mv), cudaMemcpyDeviceToHost, ctx->stream));
+        OFPSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    if (cnt > cap) {
+        set_error("%s: %zu entries, buffer holds %zu", what, cnt, cap);
+        return OFPSB_E_CAPACITY;
+    }
+    return OFPSB_OK;
+}
+}  // namespace
+
+int ofpsb_contrast_mask(ofpsb_ctx* ctx, const uint8_t* gray, int w, int h, int stride, uint8_t* mask)
+{
+    OFPSB_ENTER(ctx);
+    if (!gray || !mask || w <= 0 || h <= 0 || stride < w) {
+        set_error("contrast_mask: invalid arguments (w=%d h=%d stride=%d)", w, h, stride);
+        return OFPSB_E_INVALID;
+    }
+    int gp = 0;
+    if (int rc = upload_gray(ctx, gray, w, h, stride, &gp)) return rc;
+    if (int rc = ctx->d_cv_mask.reserve((size_t)gp * h)) return rc;
+    if (int rc = launch_contrast_mask(ctx->d_cv_gray.as<uint8_t>(), w, h, gp, ctx->d_cv_mask.as<uint8_t>(), gp, ctx->stream,
+                                      &ctx->launches))
+        return rc;
+    OFPSB_CUDA_TRY(cudaMemcpy2DAsync(mask, (size_t)w, ctx->d_cv_mask.ptr, (size_t)gp, (size_t)w, (size_t)h,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    OFPSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return OFPSB_OK;
+}
+
+int ofpsb_flow_entries_dev(ofpsb_ctx* ctx, const float* d_flow_xy, size_t flow_stride, const uint8_t* d_mask,
+                           size_t mask_stride, int w, int h, size_t gw, size_t gh, ofps_mv* d_entries, size_t cap, size_t* n)
+{
+    OFPSB_ENTER(ctx);
+    if (!d_flow_xy || (!d_entries && cap)) {
+        set_error("flow_entries: null pointer");
+        return OFPSB_E_INVALID;
+    }
+    if (int rc = ctx->d_cv_count.reserve(256)) return rc;
+    if (int rc = launch_flow_entries(d_flow_xy, flow_stride, d_mask, mask_stride, w, h, gw, gh, d_entries, cap,
+                                     ctx->d_cv_count.as<unsigned long long>(), ctx->flow, ctx->stream, &ctx->launches))
+        return rc;
+    return fetch_entries(ctx, nullptr, nullptr, cap, n, "flow_entries");
+}
+
+namespace {
+int flow_entries_host(ofpsb_ctx* ctx, const float* flow_xy, const uint8_t* d_mask, size_t mask_stride, int w, int h,
+                      size_t gw, size_t gh, ofps_mv* entries, size_t cap, size_t* n, const char* what)
+{
+    const size_t npix = (size_t)w * h;
+    const size_t max_out = gw ? gw * gh : npix;
+    const size_t dev_cap = cap < max_out ? cap : max_out;
+    if (int rc = ctx->d_cv_flow.reserve(npix * 8)) return rc;
+    if (int rc = ctx->d_entries.reserve(dev_cap * sizeof(ofps_mv))) return rc;
+    if (int rc = ctx->d_cv_count.reserve(256)) return rc;
+    OFPSB_CUDA_TRY(cudaMemcpyAsync(ctx->d_cv_flow.ptr, flow_xy, npix * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = launch_flow_entries(ctx->d_cv_flow.as<float>(), 2 * (size_t)w, d_mask, mask_stride, w, h, gw, gh,
+                                     ctx->d_entries.as<ofps_mv>(), dev_cap, ctx->d_cv_count.as<unsigned long long>(),
+                                     ctx->flow, ctx->stream, &ctx->launches))
+        return rc;
+    return fetch_entries(ctx, ctx->d_entries.as<ofps_mv>(), entries, cap, n, what);
+}
+}  // namespace
+
+int ofpsb_flow_entries(ofpsb_ctx* ctx, const float* flow_xy, const uint8_t* mask, int w, int h, size_t gw, size_t gh,
+                       ofps_mv* entries, size_t cap, size_t* n)
+{
+    OFPSB_ENTER(ctx);
+    if (!flow_xy || (!entries && cap) || w <= 0 || h <= 0) {
+        set_error("flow_entries: invalid arguments (w=%d h=%d)", w, h);
+        return OFPSB_E_INVALID;
+    }
+    const uint8_t* d_mask = nullptr;
+    if (mask) {
+        if (int rc = ctx->d_cv_mask.reserve((size_t)w * h)) return rc;
+        OFPSB_CUDA_TRY(cudaMemcpyAsync(ctx->d_cv_mask.ptr, mask, (size_t)w * h, cudaMemcpyHostToDevice, ctx->stream));
+        d_mask = ctx->d_cv_mask.as<uint8_t>();
+    }
+    return flow_entries_host(ctx, flow_xy, d_mask, (size_t)w, w, h, gw, gh, entries, cap, n, "flow_entries");
+}
+
+int ofpsb_cv_flow_frame(ofpsb_ctx* ctx, const uint8_t* gray, int gray_stride, const float* flow_xy, int w, int h,
+                        int use_mask, size_t gw, size_t gh, ofps_mv* entries, size_t cap, size_t* n)
+{
+    OFPSB_ENTER(ctx);
+    if (!flow_xy || (!entries && cap) || w <= 0 || h <= 0 || (use_mask && (!gray || gray_stride < w))) {
+        set_error("cv_flow_frame: invalid arguments (w=%d h=%d gray_stride=%d)", w, h, gray_stride);
+        return OFPSB_E_INVALID;
+    }
+    const uint8_t* d_mask = nullptr;
+    int gp = 0;
+    if (use_mask) {
+        if (int rc = upload_gray(ctx, gray, w, h, gray_stride, &gp)) return rc;
+        if (int rc = ctx->d_cv_mask.reserve((size_t)gp * h)) return rc;
+        if (int rc = launch_contrast_mask(ctx->d_cv_gray.as<uint8_t>(), w, h, gp, ctx->d_cv_mask.as<uint8_t>(), gp,
+                                          ctx->stream, &ctx->launches))
+            return rc;
+        d_mask = ctx->d_cv_mask.as<uint8_t>();
+    }
+    return flow_entries_host(ctx, flow_xy, d_mask, (size_t)gp, w, h, gw, gh, entries, cap, n, "cv_flow_frame");
 }
 
 // --------------------------------------------------------------------------- interchange files

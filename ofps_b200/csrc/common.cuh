@@ -1,7 +1,13 @@
 // Internal declarations shared by the kernels and the C ABI (api.cu).
 #pragma once
 
+#ifdef OFPSB_EMU
+#include "cuda_emu.h"   // tests/emu: CPU stand-in used by the kernel-logic tests only (never in the product build)
+#else
 #include <cuda_runtime.h>
+// Kernel launch on `stream` without dynamic shared memory; the emulation build redefines it.
+#define OFPSB_LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#endif
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -89,8 +95,9 @@ struct DensifyScratch {
 
 // entries (device) -> field (device, gw*gh*2) [+ counts]; bit-exact reference order.
 // force_path: 0 = choose by size, 1 = scan path, 2 = sort path (tests cross-check both).
+// raw != 0: d_field receives the un-divided sums (the densifier state) instead of the means.
 int launch_densify(const ofps_mv* d_entries, size_t n, size_t gw, size_t gh, float* d_field, float* d_counts,
-                   DensifyScratch& scratch, cudaStream_t stream, uint64_t* launches, int force_path = 0);
+                   DensifyScratch& scratch, cudaStream_t stream, uint64_t* launches, int force_path = 0, int raw = 0);
 
 struct DetectResult {   // written by the detector kernel (device), copied to host
     unsigned long long best_key;
@@ -105,6 +112,10 @@ int launch_detect(const float* d_mean_field, size_t dim, float target_motion, fl
                   float* d_out_field, DetectResult* d_result, DevBuf& scratch, cudaStream_t stream,
                   uint64_t* launches);
 
+// MotionFieldDensifier::interpolate_empty_cells on the host (hole_fill.cu): sequential by definition.
+// sums / counts: 2*w*h floats each (the densifier state), updated in place.
+void interpolate_empty_cells_host(float* sums, float* counts, size_t w, size_t h);
+
 // ---------------------------------------------------------------------------- almeida
 struct AlmeidaScratch {
     DevBuf state, partial, hyp, inlier_idx, flags;
@@ -113,6 +124,24 @@ struct AlmeidaScratch {
 int launch_almeida(const ofps_mv* d_entries, size_t n, float aspect, float fov_y_deg, int use_ransac,
                    size_t num_iters, float inlier_angle_deg, size_t ransac_samples, uint64_t seed,
                    float* d_quat, AlmeidaScratch& scratch, int sm_count, cudaStream_t stream, uint64_t* launches);
+
+// ---------------------------------------------------------------------------- cv-decoder front end (cv_front.cu)
+struct FlowScratch {
+    DevBuf bounds, cells, tiles;
+};
+// BGR(A)/RGB(A) u8 -> gray (OpenCV BGR2GRAY) and / or RGBA; either output may be null.
+int launch_frame_convert(const uint8_t* d_src, int w, int h, int stride, int channels, int rgb_order, uint8_t* d_gray,
+                         int gray_stride, uint8_t* d_rgba, cudaStream_t stream, uint64_t* launches);
+// resize(INTER_LINEAR), 8-bit interleaved, reductions only (OpenCV fixed-point bilinear).
+int launch_frame_resize(const uint8_t* d_src, int sw, int sh, int stride, int channels, uint8_t* d_dst, int dw, int dh,
+                        int dst_stride, cudaStream_t stream, uint64_t* launches);
+// gray -> contrast mask (0 / 255 bytes): Sobel(1,1,k5) > 20, dilated by the 11x11 ellipse, REFLECT_101 borders.
+int launch_contrast_mask(const uint8_t* d_gray, int w, int h, int stride, uint8_t* d_mask, int mask_stride,
+                         cudaStream_t stream, uint64_t* launches);
+// dense flow (+ mask) -> MotionEntry list (device), count -> *d_count.  gw == gh == 0: one entry per kept pixel.
+int launch_flow_entries(const float* d_flow, size_t flow_stride, const uint8_t* d_mask, size_t mask_stride, int w, int h,
+                        size_t gw, size_t gh, ofps_mv* d_entries, size_t cap, unsigned long long* d_count,
+                        FlowScratch& scratch, cudaStream_t stream, uint64_t* launches);
 
 }  // namespace ofpsb
 
@@ -137,5 +166,7 @@ struct ofpsb_ctx {
     ofpsb::PinBuf h_misc;
     ofpsb::DensifyScratch densify;
     ofpsb::AlmeidaScratch almeida;
+    ofpsb::FlowScratch flow;
+    ofpsb::DevBuf d_cv_src, d_cv_small, d_cv_gray, d_cv_rgba, d_cv_mask, d_cv_flow, d_cv_count;
     std::vector<cudaEvent_t> events;      // pool for the batch pipeline (no timing)
 };

@@ -42,11 +42,12 @@ __device__ __forceinline__ unsigned long long cell_of(float px, float py, float 
 }
 
 __device__ __forceinline__ void finish_cell(float sx, float sy, float cx, float cy, size_t cell, float* field,
-                                            float* counts)
+                                            float* counts, int raw)
 {
-    // MotionField::from(densifier): component_div (motion_field.rs:297-308)
-    field[2 * cell] = __fdiv_rn(sx, cx);
-    field[2 * cell + 1] = __fdiv_rn(sy, cy);
+    // MotionField::from(densifier): component_div (motion_field.rs:297-308); raw != 0 keeps the densifier's
+    // un-divided sums (the state interpolate_empty_cells works on, motion_field.rs:193-294)
+    field[2 * cell] = raw ? sx : __fdiv_rn(sx, cx);
+    field[2 * cell + 1] = raw ? sy : __fdiv_rn(sy, cy);
     if (counts) {
         counts[2 * cell] = cx;
         counts[2 * cell + 1] = cy;
@@ -58,7 +59,7 @@ constexpr float F32_EPSILON = 1.1920928955078125e-07f;
 // ------------------------------------------------------------------ scan path
 __global__ void __launch_bounds__(256) densify_scan_kernel(const ofps_mv* __restrict__ entries, size_t n, size_t gw,
                                                            size_t gh, float* __restrict__ field,
-                                                           float* __restrict__ counts)
+                                                           float* __restrict__ counts, int raw)
 {
     const unsigned lane = threadIdx.x & 31;
     const size_t cell = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(256) densify_scan_kernel(const ofps_mv* __rest
             }
         }
     }
-    if (lane == 0) finish_cell(sx, sy, cx, cy, cell, field, counts);
+    if (lane == 0) finish_cell(sx, sy, cx, cy, cell, field, counts, raw);
 }
 
 // ------------------------------------------------------------------ sort path
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const ofps_mv* __restr
                                                           const uint32_t* __restrict__ vals,
                                                           const uint32_t* __restrict__ seg_start,
                                                           const uint32_t* __restrict__ seg_end, size_t cells,
-                                                          float* __restrict__ field, float* __restrict__ counts)
+                                                          float* __restrict__ field, float* __restrict__ counts, int raw)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t cell = t / LANES;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const ofps_mv* __restr
             sx = __fadd_rn(__fmul_rn(v.z, 1.0f), sx);
             sy = __fadd_rn(__fmul_rn(v.w, 1.0f), sy);
         }
-        finish_cell(sx, sy, cx, cy, cell, field, counts);
+        finish_cell(sx, sy, cx, cy, cell, field, counts, raw);
     } else {
         for (uint32_t base = b; base < e; base += 32) {
             const uint32_t p = base + lane;
@@ -239,22 +240,22 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const ofps_mv* __restr
                 sy = __fadd_rn(__fmul_rn(my, 1.0f), sy);
             }
         }
-        if (lane == 0) finish_cell(sx, sy, cx, cy, cell, field, counts);
+        if (lane == 0) finish_cell(sx, sy, cx, cy, cell, field, counts, raw);
     }
 }
 
 __global__ void __launch_bounds__(256) empty_field_kernel(size_t cells, float* __restrict__ field,
-                                                          float* __restrict__ counts)
+                                                          float* __restrict__ counts, int raw)
 {
     const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cells) return;
-    finish_cell(0.0f, 0.0f, F32_EPSILON, F32_EPSILON, c, field, counts);
+    finish_cell(0.0f, 0.0f, F32_EPSILON, F32_EPSILON, c, field, counts, raw);
 }
 
 }  // namespace
 
 int launch_densify(const ofps_mv* d_entries, size_t n, size_t gw, size_t gh, float* d_field, float* d_counts,
-                   DensifyScratch& s, cudaStream_t stream, uint64_t* launches, int force_path)
+                   DensifyScratch& s, cudaStream_t stream, uint64_t* launches, int force_path, int raw)
 {
     if (gw == 0 || gh == 0 || gw > (1u << 24) || gh > (1u << 24) || gw * gh > 0xFFFFFFF0ull || n > 0xFFFFFFF0ull) {
         set_error("densify: invalid grid %zux%zu or n=%zu (grid sides 1..2^24, cells and n < 2^32)", gw, gh, n);
@@ -262,14 +263,14 @@ int launch_densify(const ofps_mv* d_entries, size_t n, size_t gw, size_t gh, flo
     }
     const size_t cells = gw * gh;
     if (n == 0) {
-        empty_field_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(cells, d_field, d_counts);
+        empty_field_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(cells, d_field, d_counts, raw);
         OFPSB_CUDA_TRY(cudaGetLastError());
         if (launches) ++*launches;
         return OFPSB_OK;
     }
     const bool scan = force_path == 1 || (force_path == 0 && (double)cells * (double)n <= 48.0e6);
     if (scan) {
-        densify_scan_kernel<<<(unsigned)((cells + 7) / 8), 256, 0, stream>>>(d_entries, n, gw, gh, d_field, d_counts);
+        densify_scan_kernel<<<(unsigned)((cells + 7) / 8), 256, 0, stream>>>(d_entries, n, gw, gh, d_field, d_counts, raw);
         OFPSB_CUDA_TRY(cudaGetLastError());
         if (launches) ++*launches;
         return OFPSB_OK;
@@ -306,10 +307,10 @@ int launch_densify(const ofps_mv* d_entries, size_t n, size_t gw, size_t gh, flo
     if (n / cells >= 8) {
         const size_t threads = cells * 32;
         segment_sum_kernel<32><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_entries, va, seg_start, seg_end,
-                                                                                    cells, d_field, d_counts);
+                                                                                    cells, d_field, d_counts, raw);
     } else {
         segment_sum_kernel<1><<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(d_entries, va, seg_start, seg_end,
-                                                                                  cells, d_field, d_counts);
+                                                                                  cells, d_field, d_counts, raw);
     }
     nl++;
     OFPSB_CUDA_TRY(cudaGetLastError());

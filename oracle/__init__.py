@@ -52,6 +52,8 @@ def _declare(L: C.CDLL) -> None:
     L.orc_densify.restype = None
     L.orc_flow_field.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, f32p]
     L.orc_flow_field.restype = None
+    L.orc_interpolate_empty_cells.argtypes = [f32p, f32p, C.c_size_t, C.c_size_t]
+    L.orc_interpolate_empty_cells.restype = None
     L.orc_block_dim.argtypes = [C.c_float, C.c_size_t]
     L.orc_block_dim.restype = C.c_size_t
     L.orc_detect_block_motion.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_size_t, C.c_float,
@@ -94,6 +96,8 @@ def _declare(L: C.CDLL) -> None:
     L.orc_bgr_to_gray.restype = None
     L.orc_bgr_to_rgba.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
     L.orc_bgr_to_rgba.restype = None
+    L.orc_resize_linear.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
+    L.orc_resize_linear.restype = None
     L.orc_mfield_size.argtypes = [C.c_size_t] * 6 + [szp, szp]
     L.orc_mfield_size.restype = None
     L.orc_contrast_mask.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.POINTER(C.c_int32)]
@@ -134,6 +138,13 @@ def flow_field(entries, w: int, h: int) -> np.ndarray:
     field = np.zeros((h, w, 2), np.float32)
     lib().orc_flow_field(mv.ctypes.data, len(mv), w, h, _f32p(field))
     return field
+
+
+def interpolate_empty_cells(sums: np.ndarray, counts: np.ndarray):
+    """interpolate_empty_cells (motion_field.rs:193-294) in place on sums / counts f32[h,w,2]."""
+    assert sums.dtype == np.float32 and counts.dtype == np.float32 and sums.flags.c_contiguous and counts.flags.c_contiguous
+    h, w = sums.shape[:2]
+    lib().orc_interpolate_empty_cells(_f32p(sums), _f32p(counts), w, h)
 
 
 def block_dim(min_size: float, subdivide: int) -> int:
@@ -297,6 +308,15 @@ def bgr_to_rgba(img: np.ndarray) -> np.ndarray:
     h, w, ch = img.shape
     out = np.zeros((h, w, 4), np.uint8)
     lib().orc_bgr_to_rgba(_u8p(img), w, h, w * ch, ch, _u8p(out))
+    return out
+
+
+def resize_linear(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """resize(INTER_LINEAR), 8-bit (cv-decoder/src/lib.rs:127-135)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, ch = img.shape
+    out = np.zeros((dh, dw, ch), np.uint8)
+    lib().orc_resize_linear(_u8p(img), w, h, w * ch, ch, _u8p(out), dw, dh)
     return out
 
 

@@ -72,6 +72,54 @@ void orc_mfield_size(size_t frame_w, size_t frame_h, size_t ar_x, size_t ar_y, s
     if (wb0 < hb0) { *dx = wb0; *dy = wb1; } else { *dx = hb0; *dy = hb1; }
 }
 
+/* cv-decoder/src/lib.rs:127-135: imgproc::resize(frame_tmp, frame, (dx, dy), 0, 0, INTER_LINEAR) on 8-bit pixels
+ * ("Process Fullres" off).  OpenCV's fixed-point bilinear path (resizeGeneric_, HResizeLinear / VResizeLinear,
+ * INTER_RESIZE_COEF_BITS = 11), restated and verified bit for bit against cv2 4.13:
+ *   scale = (double)src/dst;  fx = (float)((d + 0.5)*scale - 0.5);  s = floor(fx);  fx -= s;
+ *   s < 0 -> (s, fx) = (0, 0);  s >= src-1 -> (s, fx) = (src-1, 0);
+ *   a0 = cvRound((1-fx)*2048), a1 = cvRound(fx*2048)            (f32 products, round half to even, as short)
+ *   row[d] = S[s]*a0 + S[s+1]*a1                                  (int32; S[s+1] clamped, its weight is 0 there)
+ *   dst = ( ((b0*(row0 >> 4)) >> 16) + ((b1*(row1 >> 4)) >> 16) + 2 ) >> 2
+ * (An exact 2x reduction is routed to INTER_AREA by OpenCV, which gives the same values.) */
+static void resize_coeffs(int src, int dst, int *ofs, int *a0, int *a1)
+{
+    double scale = (double)src / (double)dst;
+    for (int d = 0; d < dst; d++) {
+        float fx = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(fx);
+        fx -= (float)s;
+        if (s < 0) { fx = 0.0f; s = 0; }
+        if (s >= src - 1) { fx = 0.0f; s = src - 1; }
+        ofs[d] = s;
+        a0[d] = (int)lrintf((1.0f - fx) * 2048.0f);
+        a1[d] = (int)lrintf(fx * 2048.0f);
+    }
+}
+
+void orc_resize_linear(const uint8_t *src, int sw, int sh, int stride, int channels, uint8_t *dst, int dw, int dh)
+{
+    if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return;
+    int *xo = (int *)malloc(sizeof(int) * 3 * (size_t)dw), *yo = (int *)malloc(sizeof(int) * 3 * (size_t)dh);
+    resize_coeffs(sw, dw, xo, xo + dw, xo + 2 * dw);
+    resize_coeffs(sh, dh, yo, yo + dh, yo + 2 * dh);
+    for (int y = 0; y < dh; y++) {
+        const uint8_t *r0 = src + (size_t)yo[y] * stride;
+        const uint8_t *r1 = src + (size_t)(yo[y] + 1 < sh ? yo[y] + 1 : sh - 1) * stride;
+        int b0 = yo[dh + y], b1 = yo[2 * dh + y];
+        for (int x = 0; x < dw; x++) {
+            int x0 = xo[x], x1 = x0 + 1 < sw ? x0 + 1 : sw - 1;
+            int a0 = xo[dw + x], a1 = xo[2 * dw + x];
+            for (int c = 0; c < channels; c++) {
+                int h0 = r0[x0 * channels + c] * a0 + r0[x1 * channels + c] * a1;
+                int h1 = r1[x0 * channels + c] * a0 + r1[x1 * channels + c] * a1;
+                int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                dst[((size_t)y * dw + x) * channels + c] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+            }
+        }
+    }
+    free(xo); free(yo);
+}
+
 /* cv-decoder/src/lib.rs:204-236: the contrast mask of the Farneback path.
  *   sobel  = Sobel(gray, CV_32F, dx=1, dy=1, ksize=5, scale 1, delta 0, BORDER_DEFAULT)
  *            separable kernel [-1,-2,0,2,1] in both directions (cv::getDerivKernels(1,1,5)),

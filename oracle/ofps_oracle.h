@@ -147,6 +147,8 @@ void orc_bgr_to_rgba(const uint8_t *src, int w, int h, int stride, int channels,
 /* motion-field size from frame size / aspect scale / max size (cv-decoder/src/lib.rs:90-118). */
 void orc_mfield_size(size_t frame_w, size_t frame_h, size_t ar_x, size_t ar_y, size_t max_w, size_t max_h,
                      size_t *dx, size_t *dy);
+/* resize(INTER_LINEAR) on 8-bit interleaved pixels (cv-decoder/src/lib.rs:127-135); dst = dw*dh*channels. */
+void orc_resize_linear(const uint8_t *src, int sw, int sh, int stride, int channels, uint8_t *dst, int dw, int dh);
 /* Sobel(1,1,k5) -> threshold(>20) -> dilate(11x11 ellipse), all BORDER_REFLECT_101
  * (cv-decoder/src/lib.rs:204-236).  mask: w*h bytes 0/255; sobel_out optional (w*h int32). */
 void orc_contrast_mask(const uint8_t *gray, int w, int h, int stride, uint8_t *mask, int32_t *sobel_out);

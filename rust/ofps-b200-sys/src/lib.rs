@@ -42,6 +42,31 @@ extern "C" {
         num_iters: usize, inlier_angle_deg: f32, ransac_samples: usize, seed: u64, quat_wijk: *mut f32,
     ) -> c_int;
     pub fn ofpsb_set_stream(ctx: *mut ofpsb_ctx, stream: *mut c_void) -> c_int;
+    // cv-decoder dense-flow front end (cv-decoder/src/lib.rs:84-291)
+    pub fn ofpsb_mfield_size(
+        frame_w: usize, frame_h: usize, ar_x: usize, ar_y: usize, max_w: usize, max_h: usize, dx: *mut usize,
+        dy: *mut usize,
+    ) -> c_int;
+    pub fn ofpsb_frame_convert(
+        ctx: *mut ofpsb_ctx, src: *const u8, w: c_int, h: c_int, stride: c_int, channels: c_int, rgb_order: c_int,
+        gray: *mut u8, rgba: *mut u8,
+    ) -> c_int;
+    pub fn ofpsb_frame_resize(
+        ctx: *mut ofpsb_ctx, src: *const u8, sw: c_int, sh: c_int, stride: c_int, channels: c_int, dst: *mut u8,
+        dw: c_int, dh: c_int,
+    ) -> c_int;
+    pub fn ofpsb_contrast_mask(ctx: *mut ofpsb_ctx, gray: *const u8, w: c_int, h: c_int, stride: c_int, mask: *mut u8) -> c_int;
+    pub fn ofpsb_flow_entries(
+        ctx: *mut ofpsb_ctx, flow_xy: *const f32, mask: *const u8, w: c_int, h: c_int, gw: usize, gh: usize,
+        entries: *mut ofps_mv, cap: usize, n: *mut usize,
+    ) -> c_int;
+    pub fn ofpsb_cv_flow_frame(
+        ctx: *mut ofpsb_ctx, gray: *const u8, gray_stride: c_int, flow_xy: *const f32, w: c_int, h: c_int,
+        use_mask: c_int, gw: usize, gh: usize, entries: *mut ofps_mv, cap: usize, n: *mut usize,
+    ) -> c_int;
+    // flow-extract dense field (flow-extract/src/main.rs:72-83)
+    pub fn ofpsb_flow_field(ctx: *mut ofpsb_ctx, entries: *const ofps_mv, n: usize, w: usize, h: usize, field_xy: *mut f32) -> c_int;
+    pub fn ofpsb_interpolate_empty_cells(sums_xy: *mut f32, counts_xy: *mut f32, w: usize, h: usize) -> c_int;
 }
 
 /// Owning handle.  `Send` (the reference requires plugins to be `Send`), not `Sync`: the library allows a

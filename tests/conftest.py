@@ -23,6 +23,11 @@ def oracle():
 @pytest.fixture(scope="session")
 def ctx():
     """One libofps_b200 context on cuda:0 — creation fails loudly without a B200."""
+    if os.environ.get("OFPSB_EMU_CTX") == "1":   # dry run of the cv-front GPU tests on the CPU emulation (tests/emu)
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import fake_ctx
+        yield fake_ctx.EmuContext()
+        return
     from ofps_b200 import capi
     c = capi.Context(0)
     yield c

@@ -60,5 +60,49 @@ int main(int argc, char** argv)
         if (std::strcmp(e.what(), "end of stream")) { std::printf("error: %s\n", e.what()); return 1; }
     }
     std::printf("OK frames=%d detections=%d rgba=%zu height=%zu\n", frames_with_mv, detections, rgba.size(), height);
-    return (frames_with_mv == 2 && detections == 2 && rgba.size() == (size_t)w * h && height == (size_t)h) ? 0 : 1;
+    if (!(frames_with_mv == 2 && detections == 2 && rgba.size() == (size_t)w * h && height == (size_t)h)) return 1;
+
+    // ---- DenseFlowDecoder (the cv-decoder mirror): BGR frames + a host-provided flow -> MotionEntry list
+    for (int fullres = 1; fullres >= 0; fullres--) {
+        int fno = 0;
+        auto frames = [&](std::vector<uint8_t>& bgr, int& fw, int& fh) {
+            if (fno >= 3) return false;
+            fw = w; fh = h;
+            bgr.assign((size_t)w * h * 3, 90);
+            for (int y = 100; y < 200; y++)   // a bright rectangle: its corners raise the contrast mask
+                for (int x = 150 + 4 * fno; x < 330 + 4 * fno; x++)
+                    for (int c = 0; c < 3; c++) bgr[((size_t)y * w + x) * 3 + c] = (uint8_t)(200 + 10 * c);
+            fno++;
+            return true;
+        };
+        auto flow = [&](const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, int fw, int fh, bool, bool, float* f) {
+            for (size_t i = 0; i < (size_t)fw * fh; i++) { f[2 * i] = 4.0f; f[2 * i + 1] = 0.0f; }
+        };
+        DenseFlowDecoder dd(ctx, frames, flow, 25.0);
+        dd.process_fullres = fullres != 0;
+        if (dd.props_mut().size() != 4 || std::strcmp(dd.props_mut()[3].first, "Process Fullres")) return 1;
+        int got = 0;
+        size_t last_n = 0;
+        try {
+            for (;;) {
+                mv.clear();
+                if (!dd.process_frame(mv, &rgba, &height, 0)) continue;
+                got++;
+                last_n = mv.size();
+                for (const auto& e : mv)
+                    if (!(e.px > 0 && e.px < 1 && e.py > 0 && e.py < 1 && e.my == 0.0f && e.mx > 0.0f)) return 1;
+            }
+        } catch (const Error& e) {
+            if (std::strcmp(e.what(), "Failed to grab frame")) { std::printf("error: %s\n", e.what()); return 1; }
+        }
+        const auto asp = dd.get_aspect();
+        std::printf("DENSE fullres=%d frames=%d entries=%zu aspect=%zux%zu rgba=%zu\n", fullres, got, last_n, asp->first,
+                    asp->second, rgba.size());
+        const size_t ew = fullres ? (size_t)w : 150, eh = fullres ? (size_t)h : 84;
+        if (got != 2 || last_n == 0 || last_n >= 150 * 84 || asp->first != ew || asp->second != eh || rgba.size() != ew * eh ||
+            height != eh)
+            return 1;
+    }
+    std::printf("DENSE OK\n");
+    return 0;
 }

@@ -79,6 +79,15 @@ def main():
     out["bgra"] = bgra
     out["bgra_gray"] = cv2.cvtColor(bgra, cv2.COLOR_BGRA2GRAY)
     out["rgb_gray"] = cv2.cvtColor(np.ascontiguousarray(bgra[..., :3]), cv2.COLOR_RGB2GRAY)
+    # resize(INTER_LINEAR) as cv-decoder calls it when "Process Fullres" is off (cv-decoder/src/lib.rs:127-135)
+    rz = [(300, 170, 150, 85), (257, 101, 150, 58), (160, 90, 150, 84), (64, 48, 32, 24), (50, 40, 50, 40), (97, 31, 13, 7),
+          (40, 30, 40, 15), (33, 20, 7, 20)]
+    out["resize_cases"] = np.array(rz, np.int32)
+    rng = np.random.default_rng(77)
+    for i, (sw, sh, dw, dh) in enumerate(rz):
+        src = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        out[f"rz{i}_src"] = src
+        out[f"rz{i}_dst"] = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
     # a real Farneback flow (third-party; used as INPUT of the flow -> MotionEntry stage only)
     a = scene(160, 90, 30, n_rects=10)
     b = np.roll(a, (2, -3), axis=(0, 1))

@@ -87,3 +87,13 @@ def test_flo_write(tmp_path):
         assert np.array_equal(back, field)
     except ImportError:
         pass
+
+
+def test_mfield_size_matches_reference_arithmetic():
+    """cv-decoder/src/lib.rs:90-118 — host arithmetic of the C ABI against the Python restatement."""
+    import pyref
+    for args in [(1920, 1080, 1, 1, 150, 150), (640, 360, 1, 1, 150, 150), (100, 80, 1, 1, 150, 150),
+                 (1080, 1920, 1, 1, 150, 150), (720, 576, 16, 15, 150, 100), (3840, 2160, 1, 1, 2000, 2000)]:
+        assert capi.mfield_size(*args) == tuple(pyref.mfield_size(*args)), args
+    with pytest.raises(capi.OfpsError):
+        capi.mfield_size(0, 10)

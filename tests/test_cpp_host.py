@@ -35,4 +35,4 @@ def test_cpp_host_runs(tmp_path, mode):
     exe = _build(str(tmp_path))
     p = subprocess.run([exe, mode], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
-    assert "OK frames=2 detections=2" in p.stdout
+    assert "OK frames=2 detections=2" in p.stdout and "DENSE OK" in p.stdout

@@ -141,3 +141,15 @@ def test_detector_spiral_large_grid(ctx, oracle):
     e = _cells_to_entries(cells, dim)
     has, area, d, _ = _detect_both(ctx, oracle, e, min_size=0.01, subdivide=16)
     assert d == 160 and has and area == len(cells)
+
+
+@pytest.mark.parametrize("w,h,n", [(150, 84, 880), (640, 360, 8040), (1920, 1080, 8040), (37, 23, 5), (64, 48, 0)])
+def test_flow_field_bit_exact(ctx, oracle, w, h, n):
+    """flow-extract's dense field (flow-extract/src/main.rs:72-83): GPU densifier (raw sums) + the host hole fill +
+    sum ./ counts against the oracle's densify -> interpolate_empty_cells -> finish."""
+    e = _random_entries(n, 77 + n + w)
+    got = ctx.flow_field(e, w, h)
+    want = oracle.flow_field(e, w, h)
+    assert got.tobytes() == want.tobytes()
+    if n:
+        assert np.isfinite(got).all() and (got != 0).any(axis=2).mean() > 0.99   # every hole is filled
