@@ -803,12 +803,14 @@ int ofpsb_frame_convert(ofpsb_ctx* ctx, const uint8_t* src, int w, int h, int st
         return OFPSB_E_INVALID;
     }
     const size_t npix = (size_t)w * h;
-    const int gstride = (w + 3) & ~3;
-    if (int rc = ctx->d_cv_src.reserve((size_t)stride * h)) return rc;
+    const int gstride = (w + 15) & ~15;               // 16-byte aligned device pitches: the kernel's vector path
+    const int sstride = (w * channels + 15) & ~15;
+    if (int rc = ctx->d_cv_src.reserve((size_t)sstride * h)) return rc;
     if (gray) if (int rc = ctx->d_cv_gray.reserve((size_t)gstride * h)) return rc;
     if (rgba) if (int rc = ctx->d_cv_rgba.reserve(npix * 4)) return rc;
-    OFPSB_CUDA_TRY(cudaMemcpyAsync(ctx->d_cv_src.ptr, src, (size_t)stride * h, cudaMemcpyHostToDevice, ctx->stream));
-    if (int rc = launch_frame_convert(ctx->d_cv_src.as<uint8_t>(), w, h, stride, channels, rgb_order,
+    OFPSB_CUDA_TRY(cudaMemcpy2DAsync(ctx->d_cv_src.ptr, (size_t)sstride, src, (size_t)stride, (size_t)w * channels, (size_t)h,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = launch_frame_convert(ctx->d_cv_src.as<uint8_t>(), w, h, sstride, channels, rgb_order,
                                       gray ? ctx->d_cv_gray.as<uint8_t>() : nullptr, gstride,
                                       rgba ? ctx->d_cv_rgba.as<uint8_t>() : nullptr, ctx->stream, &ctx->launches))
         return rc;

@@ -44,10 +44,30 @@ __device__ __forceinline__ void async_copy16(void* smem, const void* gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 #endif
 }
+__device__ __forceinline__ void async_copy_commit()
+{
+#ifndef OFPSB_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int PENDING>   // wait until at most PENDING of this thread's committed groups are still in flight
 __device__ __forceinline__ void async_copy_wait()
 {
 #ifndef OFPSB_EMU
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+#endif
+}
+
+// dot product of four UNSIGNED bytes (a) with four SIGNED bytes (b), plus c
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
+{
+#ifdef OFPSB_EMU
+    for (int i = 0; i < 4; i++) c += (int)((a >> (8 * i)) & 255u) * (int)(int8_t)((b >> (8 * i)) & 255u);
+    return c;
+#else
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 #endif
 }
 
@@ -59,59 +79,70 @@ __device__ __forceinline__ uint32_t gray_of(uint32_t c0, uint32_t c1, uint32_t c
     return (b * 3735u + c1 * 19235u + r * 9798u + 16384u) >> 15;
 }
 
-// One thread = 4 adjacent pixels of one row.  VEC: rows start on 4-byte boundaries (src and gray), so the
-// 12 / 16 source bytes are three / four aligned words and the four gray bytes one word store.
-template <int CH, bool VEC>
+// One thread = PX adjacent pixels of one row; blockIdx.y walks the rows (no index division).  VEC (PX = 16): rows of
+// src and gray start on 16-byte boundaries, so the 48 / 64 source bytes are three / four 16-byte loads — enough
+// bytes in flight per thread to cover the HBM latency — the 16 gray bytes one 16-byte store and the RGBA pixels
+// four.  Otherwise (PX = 4) bytes are gathered one at a time; the ragged row end always takes that path.
+template <int CH, int PX, bool VEC>
 __global__ void __launch_bounds__(256) frame_convert_kernel(const uint8_t* __restrict__ src, int w, int h, int stride,
                                                             int rgb_order, uint8_t* __restrict__ gray, int gray_stride,
-                                                            uint32_t* __restrict__ rgba)
+                                                            uint32_t* __restrict__ rgba, int rgba_vec)
 {
-    const int qpr = (w + 3) >> 2;   // pixel quads per row
-    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= (long long)qpr * h) return;
-    const int y = (int)(id / qpr), x = 4 * (int)(id % qpr);
-    const uint8_t* s = src + (size_t)y * stride + (size_t)x * CH;
-    uint32_t px[4][3];
-    const int nv = min(4, w - x);
-    if (VEC && nv == 4) {
-        const uint32_t* s4 = reinterpret_cast<const uint32_t*>(s);
-        if (CH == 3) {
-            const uint32_t a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
-            px[0][0] = a & 255u;         px[0][1] = (a >> 8) & 255u;  px[0][2] = (a >> 16) & 255u;
-            px[1][0] = a >> 24;          px[1][1] = b & 255u;         px[1][2] = (b >> 8) & 255u;
-            px[2][0] = (b >> 16) & 255u; px[2][1] = b >> 24;          px[2][2] = c & 255u;
-            px[3][0] = (c >> 8) & 255u;  px[3][1] = (c >> 16) & 255u; px[3][2] = c >> 24;
+    constexpr int NW = PX * CH / 4;   // source words per thread
+    const int x = PX * (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (x >= w) return;
+    const int nv = min(PX, w - x);
+    for (int y = blockIdx.y; y < h; y += gridDim.y) {
+        const uint8_t* s = src + (size_t)y * stride + (size_t)x * CH;
+        uint32_t wd[NW];
+        if (VEC && nv == PX) {
+#pragma unroll
+            for (int k = 0; k < NW / 4; k++) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(s) + k);
+                wd[4 * k] = v.x; wd[4 * k + 1] = v.y; wd[4 * k + 2] = v.z; wd[4 * k + 3] = v.w;
+            }
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t a = __ldg(s4 + k);
-                px[k][0] = a & 255u; px[k][1] = (a >> 8) & 255u; px[k][2] = (a >> 16) & 255u;
+            for (int k = 0; k < NW; k++) wd[k] = 0u;
+#pragma unroll
+            for (int i = 0; i < PX * CH; i++)
+                if (i < nv * CH) wd[i >> 2] |= (uint32_t)__ldg(s + i) << (8 * (i & 3));
+        }
+        // channel c of pixel k = byte k*CH + c of the thread's words
+        auto chan = [&](int k, int c) -> uint32_t { const int i = k * CH + c; return (wd[i >> 2] >> (8 * (i & 3))) & 255u; };
+        if (gray) {
+            uint32_t g[PX / 4];
+#pragma unroll
+            for (int q = 0; q < PX / 4; q++) {
+                g[q] = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    g[q] |= gray_of(chan(4 * q + j, 0), chan(4 * q + j, 1), chan(4 * q + j, 2), rgb_order != 0) << (8 * j);
+            }
+            uint8_t* o = gray + (size_t)y * gray_stride + x;
+            if (VEC && nv == PX) {
+                if (PX == 16) *reinterpret_cast<uint4*>(o) = make_uint4(g[0], g[PX / 4 > 1 ? 1 : 0], g[PX / 4 > 2 ? 2 : 0], g[PX / 4 > 3 ? 3 : 0]);
+                else *reinterpret_cast<uint32_t*>(o) = g[0];
+            } else {
+#pragma unroll
+                for (int k = 0; k < PX; k++)
+                    if (k < nv) o[k] = (uint8_t)(g[k >> 2] >> (8 * (k & 3)));
             }
         }
-    } else {
+        if (rgba) {   // RGBA::from_rgb_slice(&[bgr[2], bgr[1], bgr[0]]): r | g << 8 | b << 16 | 255 << 24 (little endian)
+            uint32_t* o = rgba + (size_t)y * w + x;
+            uint32_t e[PX];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+            for (int k = 0; k < PX; k++) e[k] = chan(k, 2) | (chan(k, 1) << 8) | (chan(k, 0) << 16) | 0xFF000000u;
+            if (VEC && PX % 4 == 0 && rgba_vec && nv == PX) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) px[k][c] = k < nv ? (uint32_t)__ldg(s + k * CH + c) : 0u;
-    }
-    if (gray) {
-        uint32_t g[4];
+                for (int q = 0; q < PX / 4; q++) reinterpret_cast<uint4*>(o)[q] = make_uint4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+            } else {
 #pragma unroll
-        for (int k = 0; k < 4; k++) g[k] = gray_of(px[k][0], px[k][1], px[k][2], rgb_order != 0);
-        uint8_t* o = gray + (size_t)y * gray_stride + x;
-        if (VEC && nv == 4) {
-            *reinterpret_cast<uint32_t*>(o) = g[0] | (g[1] << 8) | (g[2] << 16) | (g[3] << 24);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (k < nv) o[k] = (uint8_t)g[k];
+                for (int k = 0; k < PX; k++)
+                    if (k < nv) o[k] = e[k];
+            }
         }
-    }
-    if (rgba) {   // RGBA::from_rgb_slice(&[bgr[2], bgr[1], bgr[0]]): r | g << 8 | b << 16 | 255 << 24 (little endian)
-        uint32_t* o = rgba + (size_t)y * w + x;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (k < nv) o[k] = px[k][2] | (px[k][1] << 8) | (px[k][0] << 16) | 0xFF000000u;
     }
 }
 
@@ -167,10 +198,13 @@ __global__ void __launch_bounds__(256) frame_resize_kernel(const uint8_t* __rest
 constexpr int CM_TW = 256, CM_TH = 32, CM_NT = 288;
 constexpr int CM_GW = CM_TW + 32;   // gray columns t0-16 .. t0+TW+15 (apron 7, widened to whole 16-byte chunks)
 constexpr int CM_GH = CM_TH + 14;   // gray rows ty0-7 .. ty0+TH+6
-constexpr int CM_BC = CM_TW + 10;   // threshold columns t0-5 .. t0+TW+4: bit b <-> column t0-5+b
-constexpr int CM_BW = 9;            // words per threshold row (288 bits >= 266)
+constexpr int CM_BW = 9;            // words per threshold row: bit b <-> column t0-8+b (columns t0-5 .. t0+TW+4 are read)
 constexpr int CM_BH = CM_TH + 10;   // threshold rows ty0-5 .. ty0+TH+4
-static_assert(CM_NT == 32 * CM_BW, "one warp per threshold word column");
+constexpr int CM_QG = 8 * CM_BW;    // 4-pixel column groups per threshold row (72)
+constexpr int CM_QN = (8 + CM_TW + 5 + 3) / 4;   // groups that hold a column some output pixel reads (68)
+constexpr int CM_SEG = 11;          // threshold rows per row segment
+static_assert(CM_NT == 4 * CM_QG && 4 * CM_SEG >= CM_BH, "thread = (column group, one of 4 row segments)");
+static_assert(2 + CM_QN < CM_GW / 4, "the last group's right neighbour word lies inside the gray tile");
 
 __global__ void __launch_bounds__(CM_NT) contrast_mask_kernel(const uint8_t* __restrict__ gray, int w, int h, int stride,
                                                               uint8_t* __restrict__ mask, int mask_stride)
@@ -196,45 +230,72 @@ __global__ void __launch_bounds__(CM_NT) contrast_mask_kernel(const uint8_t* __r
                 for (int j = 0; j < 16; j++) G[r][16 * k + j] = __ldg(row + reflect101(x + j, w));
             }
         }
-        async_copy_wait();
+        async_copy_commit();
+        async_copy_wait<0>();
     }
     __syncthreads();
 
-    // (2) Sobel(dx=1, dy=1, ksize 5) = [-1,-2,0,2,1]^T x [-1,-2,0,2,1], threshold, ballot
+    // (2) Sobel(dx=1, dy=1, ksize 5) = [-1,-2,0,2,1]^T x [-1,-2,0,2,1], then `> 20`, four pixels per thread:
+    //     thread = (column group q of 4 adjacent pixels, row segment): 72 groups x 4 segments of 11 threshold rows.
+    //     Horizontal pass: the five taps of a pixel are one dp4a over the four bytes starting two to its left
+    //     (weights -1,-2,0,2) plus one dp4a that picks the fifth byte; +1024 keeps it positive.  Two such values
+    //     share a register as 16-bit lanes, so the vertical pass is three integer operations per pixel PAIR
+    //     (minuend and subtrahend are sums of positives: no borrow crosses the lanes), and the constant puts
+    //     `s >= 21` into bit 15 of each lane.  The four bits of a thread and the nibbles of eight adjacent
+    //     threads (redux.or) make one word of the threshold bit-plane.
     {
-        const int wc = tid >> 5, lane = tid & 31;
-        const int b = 32 * wc + lane;
-        const int px = t0 - 5 + b;
-        const int c = b + 11;   // column of px in G
-        const bool col_ok = b < CM_BC && px >= 0 && px < w;
-        int h0 = 0, h1 = 0, h2 = 0, h3 = 0;   // horizontal derivative at gray rows r-4 .. r-1
-        for (int r = 0; r < CM_GH; r++) {
-            int hr = 0;
-            if (col_ok) {
-                const uint8_t* g = &G[r][c];
-                hr = ((int)g[2] - (int)g[-2]) + 2 * ((int)g[1] - (int)g[-1]);
+        const uint32_t* Gw = reinterpret_cast<const uint32_t*>(&G[0][0]);
+        constexpr int GWW = CM_GW / 4;                  // words per gray row
+        const int q = tid % CM_QG, seg = tid / CM_QG;
+        const bool q_ok = q < CM_QN;                    // groups beyond the last needed column read nothing
+        const int wq = 2 + q;                           // word of the group's first pixel (column t0-8+4q) in a gray row
+        const int X0 = t0 - 8 + 4 * q;
+        uint32_t colmask = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) colmask |= (uint32_t)(X0 + j >= 0 && X0 + j < w) << j;
+        const int tr0 = CM_SEG * seg;
+        const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
+        uint32_t p[5][2];                               // packed horizontal derivatives of gray rows gr-4 .. gr
+#pragma unroll
+        for (int it = 0; it < CM_SEG + 4; it++) {
+            const int gr = tr0 + it;                    // gray row of this iteration
+#pragma unroll
+            for (int k = 0; k < 4; k++) { p[k][0] = p[k + 1][0]; p[k][1] = p[k + 1][1]; }
+            uint32_t W0 = 0, W1 = 0, W2 = 0;
+            if (q_ok && gr < CM_GH) {
+                const uint32_t* gw_ = Gw + gr * GWW + wq;
+                W0 = gw_[-1]; W1 = gw_[0]; W2 = gw_[1];
             }
-            if (r >= 4) {   // centre = gray row r-2 = frame row ty0-5+(r-4)
-                const int s = (hr - h0) + 2 * (h3 - h1);
-                const int py = ty0 - 5 + (r - 4);
-                const bool on = col_ok && py >= 0 && py < h && s > 20;
-                const unsigned word = __ballot_sync(0xffffffffu, on);
-                if (lane == 0) T[r - 4][wc] = word;
+            const int h0 = dp4a_us(W1, 0x00010000, dp4a_us(__funnelshift_r(W0, W1, 16), 0x0200FEFF, 1024));
+            const int h1 = dp4a_us(W1, 0x01000000, dp4a_us(__funnelshift_r(W0, W1, 24), 0x0200FEFF, 1024));
+            const int h2 = dp4a_us(W2, 0x00000001, dp4a_us(W1, 0x0200FEFF, 1024));
+            const int h3 = dp4a_us(W2, 0x00000100, dp4a_us(__funnelshift_r(W1, W2, 8), 0x0200FEFF, 1024));
+            p[4][0] = (uint32_t)h1 * 65536u + (uint32_t)h0;
+            p[4][1] = (uint32_t)h3 * 65536u + (uint32_t)h2;
+            if (it >= 4) {                              // centre = gray row gr-2 = threshold row gr-4
+                const int tr = gr - 4, py = ty0 - 5 + tr;
+                // lane = s + 32747, s = h[gr] - h[gr-4] + 2 (h[gr-1] - h[gr-3]): bit 15 <=> s > 20
+                const uint32_t slo = (p[4][0] + 2u * p[3][0] + 0x7FEB7FEBu) - (p[0][0] + 2u * p[1][0]);
+                const uint32_t shi = (p[4][1] + 2u * p[3][1] + 0x7FEB7FEBu) - (p[0][1] + 2u * p[1][1]);
+                const uint32_t v = ((slo >> 15) & 0x10001u) | (((shi >> 15) & 0x10001u) << 2);
+                uint32_t nib = (v | (v >> 15)) & colmask;
+                if (py < 0 || py >= h) nib = 0u;
+                const uint32_t word = __reduce_or_sync(gmask, nib << (4 * (tid & 7)));
+                if ((tid & 7) == 0 && tr < CM_BH) T[tr][q >> 3] = word;
             }
-            h0 = h1; h1 = h2; h2 = h3; h3 = hr;
         }
     }
     __syncthreads();
 
-    // (3) out-of-frame threshold positions take the bit of their reflection (dilate's BORDER_REFLECT_101)
-    if (t0 - 5 < 0 || t0 + CM_TW + 5 > w || ty0 - 5 < 0 || ty0 + CM_TH + 5 > h) {
-        for (int i = tid; i < CM_BH * CM_BC; i += CM_NT) {
-            const int br = i / CM_BC, b = i % CM_BC;
-            const int px = t0 - 5 + b, py = ty0 - 5 + br;
-            if (px >= 0 && px < w && py >= 0 && py < h) continue;
-            const int qb = reflect101(px, w) - (t0 - 5), qr = reflect101(py, h) - (ty0 - 5);
-            if (qb < 0 || qb >= CM_BC || qr < 0 || qr >= CM_BH) continue;   // read by no in-frame pixel of this tile
-            if ((T[qr][qb >> 5] >> (qb & 31)) & 1u) atomicOr(&T[br][b >> 5], 1u << (b & 31));
+    // (3) dilate's BORDER_REFLECT_101: rows are reflected by index in (4); out-of-frame COLUMNS take the bit of
+    //     their reflection here (at most five on either side of the frame)
+    if (t0 == 0 || w < t0 + CM_TW + 5) {
+        for (int i = tid; i < CM_BH * 10; i += CM_NT) {
+            const int br = i / 10, k = i - br * 10;
+            const int X = k < 5 ? k - 5 : w + (k - 5);
+            const int b = X - (t0 - 8), qb = reflect101(X, w) - (t0 - 8);
+            if (b < 0 || b >= 32 * CM_BW || qb < 0 || qb >= 32 * CM_BW) continue;   // not in this tile / read by no pixel of it
+            if ((T[br][qb >> 5] >> (qb & 31)) & 1u) atomicOr(&T[br][b >> 5], 1u << (b & 31));
         }
         __syncthreads();
     }
@@ -244,21 +305,23 @@ __global__ void __launch_bounds__(CM_NT) contrast_mask_kernel(const uint8_t* __r
         const int orow = tid >> 3, ow = tid & 7;
         const int y = ty0 + orow, x0 = t0 + 32 * ow;
         if (y < h && x0 < w) {
-            // 64-bit window of threshold row dy: bit i <-> column x0-5+i
+            // 64-bit window of the threshold row of frame row y+dy (reflected into the frame): bit i <-> column x0-8+i
             auto win = [&](int dy) -> unsigned long long {
-                const uint32_t* t = T[orow + 5 + dy];
+                int py = y + dy;
+                if (py < 0 || py >= h) py = reflect101(py, h);
+                const uint32_t* t = T[py - (ty0 - 5)];
                 return (unsigned long long)t[ow] | ((unsigned long long)t[ow + 1] << 32);
             };
             const unsigned long long v5 = win(-2) | win(-1) | win(0) | win(1) | win(2);
             const unsigned long long v4 = win(-3) | win(3), v3 = win(-4) | win(4), v0 = win(-5) | win(5);
-            // run-OR of n = 2k+1 consecutive bits, then >> (5-k) centres it on the output pixel
+            // run-OR of n = 2k+1 consecutive bits, then >> (8-k) centres it on the output pixel
             const unsigned long long a2 = v5 | (v5 >> 1), a4 = a2 | (a2 >> 2), a8 = a4 | (a4 >> 4);
-            uint32_t m = (uint32_t)(a8 | (a4 >> 7));                           // k = 5: 11 bits
+            uint32_t m = (uint32_t)((a8 | (a4 >> 7)) >> 3);                    // k = 5: 11 bits
             const unsigned long long b2 = v4 | (v4 >> 1), b4 = b2 | (b2 >> 2), b8 = b4 | (b4 >> 4);
-            m |= (uint32_t)((b8 | (v4 >> 8)) >> 1);                            // k = 4: 9 bits
+            m |= (uint32_t)((b8 | (v4 >> 8)) >> 4);                            // k = 4: 9 bits
             const unsigned long long c2 = v3 | (v3 >> 1), c4 = c2 | (c2 >> 2);
-            m |= (uint32_t)((c4 | (c4 >> 3)) >> 2);                            // k = 3: 7 bits
-            m |= (uint32_t)(v0 >> 5);                                          // k = 0
+            m |= (uint32_t)((c4 | (c4 >> 3)) >> 5);                            // k = 3: 7 bits
+            m |= (uint32_t)(v0 >> 8);                                          // k = 0
             uint8_t* o = mask + (size_t)y * mask_stride + x0;
             if (x0 + 32 <= w && ((reinterpret_cast<uintptr_t>(mask) | (uintptr_t)mask_stride) & 15u) == 0) {
                 uint32_t e[8];
@@ -286,100 +349,129 @@ __device__ __forceinline__ int cell_coord(int x, float inv, float gm1)
     return v > 0.0f ? (int)v : 0;
 }
 
-// starts[c] = first pixel coordinate whose cell index is >= c, c = 0..g (starts[g] = len).
-__global__ void cell_bounds_kernel(int w, int h, int gw, int gh, int* __restrict__ xs, int* __restrict__ ys)
+// First pixel coordinate whose cell index is >= c (len if there is none): binary search on the monotone cell_coord.
+__device__ __forceinline__ int cell_start(int c, int len, float inv, float gm1)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= w) {
-        const float inv = __fdiv_rn(1.0f, (float)w), gm1 = (float)(gw - 1);
-        const int c = i < w ? cell_coord(i, inv, gm1) : gw;
-        const int cp = i > 0 ? cell_coord(i - 1, inv, gm1) : -1;
-        for (int k = cp + 1; k <= c && k <= gw; k++) xs[k] = i;
-    } else if (i - (w + 1) <= h) {
-        const int j = i - (w + 1);
-        const float inv = __fdiv_rn(1.0f, (float)h), gm1 = (float)(gh - 1);
-        const int c = j < h ? cell_coord(j, inv, gm1) : gh;
-        const int cp = j > 0 ? cell_coord(j - 1, inv, gm1) : -1;
-        for (int k = cp + 1; k <= c && k <= gh; k++) ys[k] = j;
+    int lo = 0, hi = len;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cell_coord(mid, inv, gm1) >= c) hi = mid;
+        else lo = mid + 1;
     }
+    return lo;
 }
 
 constexpr float F32_EPSILON = 1.1920928955078125e-07f;
-constexpr int FC_NT = 64;         // threads per CTA (all stage pixels; the first FC_NC fold)
-constexpr int FC_NC = 16;         // cells per CTA (of one cell row): small CTAs, many resident per SM, so the
-                                  // sequential folds of some overlap the loads of others
-constexpr int FC_CAP = 2048;      // pixels staged per step (16 KB of flow + 2 KB of mask)
+constexpr int FC_NT = 128;        // threads per CTA: all of them issue the copies, warp 0 folds
+constexpr int FC_NC = 32;         // cells per CTA (adjacent cells of one cell row), one lane each
+constexpr int FC_CAP = 2048;      // pixels per staging buffer (16 KB of flow)
+constexpr int FC_MCAP = 4096;     // mask bytes per staging buffer
 
 struct CellRec { float mx, my; uint32_t touched, pad; };
 
-// One CTA = FC_NC adjacent cells of one cell row.  The pixel rectangle of those cells is staged through
-// shared memory with coalesced loads (several image rows per step when the span is narrow); thread t then
-// folds the pixels of cell t in raster order — rows top to bottom, columns left to right — which is the
-// order in which the reference's loop reaches that cell, so sums and counts are bit-identical:
-//   counts += 1.0 (from f32::EPSILON), sum = motion * 1.0 + sum, motion = flow .* (1/W, 1/H).
-template <bool ASYNC>   // ASYNC: flow rows are 8-byte aligned -> staged by asynchronous 8-byte copies
+// One CTA = FC_NC adjacent cells of one cell row.  Their pixel rectangle is streamed through two shared-memory
+// buffers: while warp 0 folds the rows of one buffer, the copies of the next step are already in flight
+// (ASYNC: 16-byte asynchronous copies, two flow pixels / sixteen mask bytes each, starting at the aligned
+// address below the first pixel).  Lane t folds the pixels of cell t in raster order — rows top to bottom,
+// columns left to right — which is the order in which the reference's loop reaches that cell, so sums and counts
+// are bit-identical:  counts += 1.0 (from f32::EPSILON), sum = motion * 1.0 + sum, motion = flow .* (1/W, 1/H).
+template <bool ASYNC>
 __global__ void __launch_bounds__(FC_NT) flow_cells_kernel(const float* __restrict__ flow, long long flow_stride,
                                                            const uint8_t* __restrict__ mask, long long mask_stride,
-                                                           int w, int h, int gw, int gh, const int* __restrict__ xs,
-                                                           const int* __restrict__ ys, CellRec* __restrict__ cells)
+                                                           int w, int h, int gw, int gh, CellRec* __restrict__ cells)
 {
-    __shared__ float2 sflow[FC_CAP];
-    __shared__ uint8_t smask[FC_CAP];
+    __shared__ __align__(16) float2 sflow[2][FC_CAP];
+    __shared__ __align__(16) uint8_t smask[2][FC_MCAP];
+    __shared__ int sxs[FC_NC + 1], sys_[2];
     const int tid = threadIdx.x;
     const int cy = blockIdx.y, c0 = blockIdx.x * FC_NC, c1 = min(c0 + FC_NC, gw);
-    const int y0 = ys[cy], y1 = ys[cy + 1];
-    const int px0 = xs[c0], px1 = xs[c1];
+    const float nx = __fdiv_rn(1.0f, (float)w), ny = __fdiv_rn(1.0f, (float)h);
+    if (tid <= FC_NC) sxs[tid] = cell_start(min(c0 + tid, gw), w, nx, (float)(gw - 1));
+    else if (tid < FC_NC + 3) sys_[tid - FC_NC - 1] = cell_start(cy + tid - FC_NC - 1, h, ny, (float)(gh - 1));
+    __syncthreads();
+    const int y0 = sys_[0], y1 = sys_[1];
+    const int px0 = sxs[0], px1 = sxs[c1 - c0];
     const int cell = c0 + tid;
     const bool owner = tid < FC_NC && cell < c1;
-    const int xa = owner ? xs[cell] : 0, xb = owner ? xs[cell + 1] : 0;
-    const float nx = __fdiv_rn(1.0f, (float)w), ny = __fdiv_rn(1.0f, (float)h);
+    const int xa = owner ? sxs[tid] : 0, xb = owner ? sxs[tid + 1] : 0;
     float sx = 0.0f, sy = 0.0f, cnt = F32_EPSILON;
-    uint32_t hits = 0;
-    const int span = px1 - px0;
-    if (span > 0 && y1 > y0) {
-        const int cw = min(span, FC_CAP);
-        const int rg = max(1, FC_CAP / cw);   // rows per step; > 1 only when the whole span fits (cw == span)
-        for (int r0 = y0; r0 < y1; r0 += rg) {
-            const int nr = min(rg, y1 - r0);
-            for (int cx0 = px0; cx0 < px1; cx0 += cw) {
-                const int nc = min(cw, px1 - cx0);
+    const int span = px1 - px0, rows = y1 - y0;
+    if (span > 0 && rows > 0) {
+        const int cw = min(span, FC_CAP - 4);          // pixels per row of one step
+        const int pitchf = (cw + 3) & ~1;              // row pitch of the flow buffer (pixels; even, >= cw + 2)
+        const int pitchm = (cw + 30) & ~15;            // row pitch of the mask buffer (bytes; multiple of 16, >= cw + 15)
+        const int rg = max(1, min(FC_CAP / pitchf, FC_MCAP / pitchm));   // rows per step; > 1 only when cw == span
+        const int ncs = (span + cw - 1) / cw, nrs = (rows + rg - 1) / rg, nsteps = ncs * nrs;
+        auto stage = [&](int s) {   // issue the copies of step s into buffer s & 1
+            const int ri = s / ncs, ci = s - ri * ncs;
+            const int r0 = y0 + ri * rg, nr = min(rg, y1 - r0);
+            const int cx0 = px0 + ci * cw, nc = min(cw, px1 - cx0);
+            float2* sf = sflow[s & 1];
+            uint8_t* sm = smask[s & 1];
+            if (ASYNC) {
+                const int ax0 = cx0 & ~1, nf = (cx0 + nc - ax0 + 1) >> 1;
+                for (int r = 0; r < nr; r++) {
+                    const float* frow = flow + (long long)(r0 + r) * flow_stride + 2ll * ax0;
+                    for (int k = tid; k < nf; k += FC_NT) async_copy16(sf + r * pitchf + 2 * k, frow + 4 * k);
+                }
+                if (mask) {
+                    const int am0 = cx0 & ~15, nm = (cx0 + nc - am0 + 15) >> 4;
+                    for (int r = 0; r < nr; r++) {
+                        const uint8_t* mrow = mask + (long long)(r0 + r) * mask_stride + am0;
+                        for (int k = tid; k < nm; k += FC_NT) async_copy16(sm + r * pitchm + 16 * k, mrow + 16 * k);
+                    }
+                }
+            } else {
                 for (int r = 0; r < nr; r++) {
                     const float* frow = flow + (long long)(r0 + r) * flow_stride + 2ll * cx0;
-                    float2* srow = sflow + r * cw;
-                    for (int c = tid; c < nc; c += FC_NT) {
-                        if (ASYNC) async_copy8(srow + c, frow + 2 * c);
-                        else srow[c] = make_float2(__ldg(frow + 2 * c), __ldg(frow + 2 * c + 1));
-                    }
-                }
-                if (mask)
-                    for (int r = 0; r < nr; r++) {
+                    for (int c = tid; c < nc; c += FC_NT) sf[r * pitchf + c] = make_float2(__ldg(frow + 2 * c), __ldg(frow + 2 * c + 1));
+                    if (mask) {
                         const uint8_t* mrow = mask + (long long)(r0 + r) * mask_stride + cx0;
-#pragma unroll 4
-                        for (int c = tid; c < nc; c += FC_NT) smask[r * cw + c] = __ldg(mrow + c);
+                        for (int c = tid; c < nc; c += FC_NT) sm[r * pitchm + c] = __ldg(mrow + c);
                     }
-                if (ASYNC) async_copy_wait();
-                __syncthreads();
-                if (owner) {
-                    const int a = max(xa, cx0) - cx0, b = min(xb, cx0 + nc) - cx0;
-                    for (int r = 0; r < nr; r++)
-                        for (int c = a; c < b; c++) {
-                            if (mask && smask[r * cw + c] == 0) continue;   // `*mask < 0.1` -> skip (cv-decoder:258)
-                            const float2 f = sflow[r * cw + c];
-                            cnt = __fadd_rn(cnt, 1.0f);
-                            sx = __fadd_rn(__fmul_rn(f.x, nx), sx);
-                            sy = __fadd_rn(__fmul_rn(f.y, ny), sy);
-                            hits++;
-                        }
                 }
-                __syncthreads();
             }
+            async_copy_commit();
+        };
+        stage(0);
+        for (int s = 0; s < nsteps; s++) {
+            if (s + 1 < nsteps) {
+                stage(s + 1);
+                async_copy_wait<1>();   // everything but the copies just issued has landed
+            } else {
+                async_copy_wait<0>();
+            }
+            __syncthreads();
+            if (owner) {
+                const int ri = s / ncs, ci = s - ri * ncs;
+                const int r0 = y0 + ri * rg, nr = min(rg, y1 - r0);
+                const int cx0 = px0 + ci * cw, nc = min(cw, px1 - cx0);
+                const int a = max(xa, cx0) - cx0, b = min(xb, cx0 + nc) - cx0;
+                const float2* sf = sflow[s & 1] + (ASYNC ? (cx0 & 1) : 0);
+                const uint8_t* sm = smask[s & 1] + (ASYNC ? (cx0 & 15) : 0);
+                for (int r = 0; r < nr; r++) {
+                    const float2* fr = sf + r * pitchf;
+                    const uint8_t* mr = sm + r * pitchm;
+#pragma unroll 4
+                    for (int c = a; c < b; c++) {
+                        const bool keep = !mask || mr[c] != 0;   // `*mask < 0.1` -> skip (cv-decoder:258)
+                        const float2 f = fr[c];
+                        const float ncnt = __fadd_rn(cnt, 1.0f);
+                        const float nsx = __fadd_rn(__fmul_rn(f.x, nx), sx), nsy = __fadd_rn(__fmul_rn(f.y, ny), sy);
+                        cnt = keep ? ncnt : cnt;
+                        sx = keep ? nsx : sx;
+                        sy = keep ? nsy : sy;
+                    }
+                }
+            }
+            __syncthreads();   // buffer s & 1 is free for the copies of step s + 2
         }
     }
     if (owner) {
         CellRec rec;
         rec.mx = __fdiv_rn(sx, cnt);   // MotionField::from(densifier): sum ./ counts
         rec.my = __fdiv_rn(sy, cnt);
-        rec.touched = hits ? 1u : 0u;
+        rec.touched = cnt > 0.5f ? 1u : 0u;   // counts start at f32::EPSILON and grow by 1.0 per vector
         rec.pad = 0u;
         cells[(size_t)cy * gw + cell] = rec;
     }
@@ -409,7 +501,9 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_t
 }
 
 // Touched cells in (x, y) lexicographic order (BTreeSet<(usize, usize)>, cv-decoder:243, 276) -> entries:
-// pos = (x + 0.5, y + 0.5) .* (1/gw, 1/gh), motion = cell mean.  One CTA walks the column-major index.
+// pos = (x + 0.5, y + 0.5) .* (1/gw, 1/gh), motion = cell mean.  One CTA; every thread owns FE_PER consecutive
+// positions of the column-major order per pass: independent flag loads, one block scan per pass, ordered writes.
+constexpr int FE_PER = 8;
 __global__ void __launch_bounds__(1024) flow_emit_cells_kernel(const CellRec* __restrict__ cells, int gw, int gh,
                                                                ofps_mv* __restrict__ out, unsigned long long cap,
                                                                unsigned long long* __restrict__ n_out)
@@ -418,25 +512,35 @@ __global__ void __launch_bounds__(1024) flow_emit_cells_kernel(const CellRec* __
     const float gx = __fdiv_rn(1.0f, (float)gw), gy = __fdiv_rn(1.0f, (float)gh);
     const long long total = (long long)gw * gh;
     unsigned long long base = 0;
-    for (long long k0 = 0; k0 < total; k0 += blockDim.x) {
-        const long long k = k0 + threadIdx.x;
-        int x = 0, y = 0;
-        CellRec rec = {0.f, 0.f, 0u, 0u};
-        if (k < total) {
-            x = (int)(k / gh);
-            y = (int)(k - (long long)x * gh);
-            rec = cells[(size_t)y * gw + x];
+    for (long long k0 = 0; k0 < total; k0 += (long long)blockDim.x * FE_PER) {
+        const long long kb = k0 + (long long)threadIdx.x * FE_PER;
+        uint32_t flags = 0;
+#pragma unroll
+        for (int j = 0; j < FE_PER; j++) {
+            const long long k = kb + j;
+            if (k < total) {
+                const int x = (int)(k / gh), y = (int)(k - (long long)x * gh);
+                flags |= (cells[(size_t)y * gw + x].touched & 1u) << j;
+            }
         }
         uint32_t tot;
-        const uint32_t rank = block_excl_scan(rec.touched, warp_tot, &tot);
-        if (rec.touched && base + rank < cap) {
-            ofps_mv e;
-            e.px = __fmul_rn(__fadd_rn((float)x, 0.5f), gx);
-            e.py = __fmul_rn(__fadd_rn((float)y, 0.5f), gy);
-            e.mx = rec.mx;
-            e.my = rec.my;
-            out[base + rank] = e;
-        }
+        unsigned long long pos = base + block_excl_scan(__popc(flags), warp_tot, &tot);
+#pragma unroll
+        for (int j = 0; j < FE_PER; j++)
+            if ((flags >> j) & 1u) {
+                const long long k = kb + j;
+                const int x = (int)(k / gh), y = (int)(k - (long long)x * gh);
+                if (pos < cap) {
+                    const CellRec rec = cells[(size_t)y * gw + x];
+                    ofps_mv e;
+                    e.px = __fmul_rn(__fadd_rn((float)x, 0.5f), gx);
+                    e.py = __fmul_rn(__fadd_rn((float)y, 0.5f), gy);
+                    e.mx = rec.mx;
+                    e.my = rec.my;
+                    out[pos] = e;
+                }
+                pos++;
+            }
         base += tot;
     }
     if (threadIdx.x == 0) *n_out = base;
@@ -535,17 +639,18 @@ int launch_frame_convert(const uint8_t* d_src, int w, int h, int stride, int cha
         return OFPSB_E_INVALID;
     }
     if (!d_gray && !d_rgba) return OFPSB_OK;
-    const bool vec = ((reinterpret_cast<uintptr_t>(d_src) | (uintptr_t)stride) & 3u) == 0 &&
-                     (!d_gray || ((reinterpret_cast<uintptr_t>(d_gray) | (uintptr_t)gray_stride) & 3u) == 0);
-    const long long quads = (long long)((w + 3) / 4) * h;
-    const unsigned grid = (unsigned)((quads + 255) / 256);
+    const bool vec = ((reinterpret_cast<uintptr_t>(d_src) | (uintptr_t)stride) & 15u) == 0 &&
+                     (!d_gray || ((reinterpret_cast<uintptr_t>(d_gray) | (uintptr_t)gray_stride) & 15u) == 0);
+    const int rgba_vec = d_rgba && (reinterpret_cast<uintptr_t>(d_rgba) & 15u) == 0 && (w & 3) == 0;
     uint32_t* rgba = reinterpret_cast<uint32_t*>(d_rgba);
+    const int px = vec ? 16 : 4;
+    const dim3 grid((unsigned)(((w + px - 1) / px + 255) / 256), (unsigned)(h < 65535 ? h : 65535));
     if (channels == 3) {
-        if (vec) OFPSB_LAUNCH((frame_convert_kernel<3, true>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba);
-        else OFPSB_LAUNCH((frame_convert_kernel<3, false>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba);
+        if (vec) OFPSB_LAUNCH((frame_convert_kernel<3, 16, true>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
+        else OFPSB_LAUNCH((frame_convert_kernel<3, 4, false>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
     } else {
-        if (vec) OFPSB_LAUNCH((frame_convert_kernel<4, true>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba);
-        else OFPSB_LAUNCH((frame_convert_kernel<4, false>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba);
+        if (vec) OFPSB_LAUNCH((frame_convert_kernel<4, 16, true>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
+        else OFPSB_LAUNCH((frame_convert_kernel<4, 4, false>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
     }
     OFPSB_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;
@@ -639,22 +744,21 @@ int launch_flow_entries(const float* d_flow, size_t flow_stride, const uint8_t* 
         return OFPSB_OK;
     }
     const int igw = (int)gw, igh = (int)gh;
-    if (int rc = scratch.bounds.reserve((gw + gh + 2) * sizeof(int))) return rc;
     if (int rc = scratch.cells.reserve(gw * gh * sizeof(CellRec))) return rc;
-    int* xs = scratch.bounds.as<int>();
-    int* ys = xs + gw + 1;
     CellRec* cells = scratch.cells.as<CellRec>();
-    OFPSB_LAUNCH(cell_bounds_kernel, (unsigned)((w + h + 2 + 255) / 256), 256, stream, w, h, igw, igh, xs, ys);
     const dim3 grid((unsigned)((igw + FC_NC - 1) / FC_NC), (unsigned)igh);
-    if (((reinterpret_cast<uintptr_t>(d_flow) & 7u) | (flow_stride & 1u)) == 0)
+    // 16-byte asynchronous staging needs 16-byte aligned flow rows (and mask rows, when there is a mask)
+    const bool async = ((reinterpret_cast<uintptr_t>(d_flow) & 15u) | (flow_stride & 3u)) == 0 &&
+                       (!d_mask || ((reinterpret_cast<uintptr_t>(d_mask) & 15u) | (mask_stride & 15u)) == 0);
+    if (async)
         OFPSB_LAUNCH(flow_cells_kernel<true>, grid, FC_NT, stream, d_flow, (long long)flow_stride, d_mask, (long long)mask_stride, w,
-                     h, igw, igh, xs, ys, cells);
+                     h, igw, igh, cells);
     else
         OFPSB_LAUNCH(flow_cells_kernel<false>, grid, FC_NT, stream, d_flow, (long long)flow_stride, d_mask, (long long)mask_stride, w,
-                     h, igw, igh, xs, ys, cells);
+                     h, igw, igh, cells);
     OFPSB_LAUNCH(flow_emit_cells_kernel, 1, 1024, stream, cells, igw, igh, d_entries, cap, d_count);
     OFPSB_CUDA_TRY(cudaGetLastError());
-    if (launches) *launches += 3;
+    if (launches) *launches += 2;
     return OFPSB_OK;
 }
 

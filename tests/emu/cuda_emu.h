@@ -108,6 +108,14 @@ inline uint32_t __reduce_add_sync(unsigned, uint32_t v)
     for (int i = 0; i < 32; i++) s += t[i];
     return s;
 }
+inline uint32_t __reduce_or_sync(unsigned mask, uint32_t v)   // subgroup masks: every lane passes the mask of its own group
+{
+    uint32_t t[32], s = 0;
+    emu_exchange(v, t);
+    for (int i = 0; i < 32; i++)
+        if ((mask >> i) & 1u) s |= t[i];
+    return s;
+}
 inline uint32_t __reduce_min_sync(unsigned, uint32_t v)
 {
     uint32_t t[32], s = 0xffffffffu;
@@ -124,6 +132,8 @@ inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline int __float2int_rn(float a) { return (int)lrintf(a); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((unsigned long long)hi << 32) | lo) >> (sh & 31)); }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 using std::max;

@@ -76,6 +76,22 @@ def test_emu_frame_convert(emu, gold, oracle):
             assert np.array_equal(rgba, oracle.bgr_to_rgba(img))
 
 
+@pytest.mark.parametrize("w,h,ch,pitch,gpitch", [(64, 5, 3, 192, 64), (80, 3, 4, 320, 80), (53, 4, 3, 160, 64), (20, 3, 4, 80, 32),
+                                                  (16, 2, 3, 48, 16), (100, 2, 3, 304, 112)])
+def test_emu_frame_convert_vector_path(emu, oracle, w, h, ch, pitch, gpitch):
+    """16-byte aligned pitches: the 16-pixel vector path, its ragged row end and the vector / scalar RGBA stores."""
+    rng = np.random.default_rng(w * ch)
+    buf = rng.integers(0, 256, (h, pitch), dtype=np.uint8)
+    img = np.ascontiguousarray(buf[:, :w * ch].reshape(h, w, ch))
+    assert buf.ctypes.data % 16 == 0
+    for rgb in (0, 1):
+        gray = np.full((h, gpitch), 3, np.uint8)
+        rgba = np.zeros((h, w, 4), np.uint8)
+        assert emu.emu_frame_convert(_u8(buf), w, h, pitch, ch, rgb, _u8(gray), gpitch, _u8(rgba)) == 0
+        assert np.array_equal(gray[:, :w], oracle.bgr_to_gray(img, bool(rgb))) and (gray[:, w:] == 3).all()
+        assert np.array_equal(rgba, oracle.bgr_to_rgba(img))
+
+
 def test_emu_frame_resize(emu, gold, oracle):
     for i, (sw, sh, dw, dh) in enumerate(gold["resize_cases"]):
         src = np.ascontiguousarray(gold[f"rz{i}_src"])

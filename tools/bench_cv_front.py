@@ -123,7 +123,7 @@ def main():
         t_cpu = cpu_time(lambda: oracle.flow_entries(flow, mask, gw, gh)) if name != "8K" else None
         emit(case=f"K9 flow_entries (mask, {gw}x{gh} densifier) {name}", us=t * 1e6, launches=nl, mpix_s=npix / t / 1e6,
              roofline=roof(9 * npix + 16 * n, t), entries=n, cpu_oracle_ms=t_cpu and t_cpu * 1e3,
-             note="time includes the 8-byte count read-back the C ABI performs (one stream sync)")
+             note="two launches; time includes the 8-byte count read-back the C ABI performs (one stream sync)")
         # K9 without mask (RLOF path)
         n = ctx.flow_entries_dev(d_flow, 2 * w, None, 0, w, h, gw, gh, d_ent, gw * gh)
         t, nl = dev_time(lambda: launch_flow(ctx, d_flow, w, h, None, gw, gh, d_ent))
