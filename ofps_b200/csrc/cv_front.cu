@@ -71,20 +71,29 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
 #endif
 }
 
-// ------------------------------------------------------------------------------------------ K7
-// OpenCV 4.x 8-bit BGR2GRAY: (B*3735 + G*19235 + R*9798 + 2^14) >> 15.
-__device__ __forceinline__ uint32_t gray_of(uint32_t c0, uint32_t c1, uint32_t c2, bool rgb_order)
+// c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (LO) or ... * b.byte2, b.byte3 (HI), everything unsigned
+template <bool HI>
+__device__ __forceinline__ uint32_t dp2a_uu(uint32_t a, uint32_t b, uint32_t c)
 {
-    const uint32_t b = rgb_order ? c2 : c0, r = rgb_order ? c0 : c2;
-    return (b * 3735u + c1 * 19235u + r * 9798u + 16384u) >> 15;
+#ifdef OFPSB_EMU
+    const int o = HI ? 16 : 0;
+    return c + (a & 0xFFFFu) * ((b >> o) & 255u) + (a >> 16) * ((b >> (o + 8)) & 255u);
+#else
+    uint32_t d;
+    if (HI) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    else asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+#endif
 }
 
+// ------------------------------------------------------------------------------------------ K7
+// OpenCV 4.x 8-bit BGR2GRAY: (B*3735 + G*19235 + R*9798 + 2^14) >> 15.
 // One thread = PX adjacent pixels of one row; blockIdx.y walks the rows (no index division).  VEC (PX = 16): rows of
 // src and gray start on 16-byte boundaries, so the 48 / 64 source bytes are three / four 16-byte loads — enough
 // bytes in flight per thread to cover the HBM latency — the 16 gray bytes one 16-byte store and the RGBA pixels
 // four.  Otherwise (PX = 4) bytes are gathered one at a time; the ragged row end always takes that path.
 template <int CH, int PX, bool VEC>
-__global__ void __launch_bounds__(256) frame_convert_kernel(const uint8_t* __restrict__ src, int w, int h, int stride,
+__global__ void __launch_bounds__(128) frame_convert_kernel(const uint8_t* __restrict__ src, int w, int h, int stride,
                                                             int rgb_order, uint8_t* __restrict__ gray, int gray_stride,
                                                             uint32_t* __restrict__ rgba, int rgba_vec)
 {
@@ -108,16 +117,25 @@ __global__ void __launch_bounds__(256) frame_convert_kernel(const uint8_t* __res
             for (int i = 0; i < PX * CH; i++)
                 if (i < nv * CH) wd[i >> 2] |= (uint32_t)__ldg(s + i) << (8 * (i & 3));
         }
-        // channel c of pixel k = byte k*CH + c of the thread's words
-        auto chan = [&](int k, int c) -> uint32_t { const int i = k * CH + c; return (wd[i >> 2] >> (8 * (i & 3))) & 255u; };
+        // pixel k as one word (c0, c1, c2, x): its three channels start at byte k*CH of the thread's words
+        auto pixel = [&](int k) -> uint32_t {
+            if (CH == 4) return wd[k];
+            const int i = (3 * k) >> 2, sh = 8 * ((3 * k) & 3);
+            return sh == 0 ? wd[i] : __funnelshift_r(wd[i], wd[i + 1 < NW ? i + 1 : i], sh);
+        };
+        // luma weights as 16-bit pairs for dp2a: (c0, c1) and (c2, -)
+        const uint32_t k01 = rgb_order ? (9798u | (19235u << 16)) : (3735u | (19235u << 16));
+        const uint32_t k2 = rgb_order ? 3735u : 9798u;
         if (gray) {
             uint32_t g[PX / 4];
 #pragma unroll
             for (int q = 0; q < PX / 4; q++) {
                 g[q] = 0u;
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    g[q] |= gray_of(chan(4 * q + j, 0), chan(4 * q + j, 1), chan(4 * q + j, 2), rgb_order != 0) << (8 * j);
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t p = pixel(4 * q + j);
+                    g[q] |= (dp2a_uu<true>(k2, p, dp2a_uu<false>(k01, p, 16384u)) >> 15) << (8 * j);
+                }
             }
             uint8_t* o = gray + (size_t)y * gray_stride + x;
             if (VEC && nv == PX) {
@@ -129,11 +147,11 @@ __global__ void __launch_bounds__(256) frame_convert_kernel(const uint8_t* __res
                     if (k < nv) o[k] = (uint8_t)(g[k >> 2] >> (8 * (k & 3)));
             }
         }
-        if (rgba) {   // RGBA::from_rgb_slice(&[bgr[2], bgr[1], bgr[0]]): r | g << 8 | b << 16 | 255 << 24 (little endian)
+        if (rgba) {   // RGBA::from_rgb_slice(&[bgr[2], bgr[1], bgr[0]]): (c2, c1, c0, 255) as bytes 0..3
             uint32_t* o = rgba + (size_t)y * w + x;
             uint32_t e[PX];
 #pragma unroll
-            for (int k = 0; k < PX; k++) e[k] = chan(k, 2) | (chan(k, 1) << 8) | (chan(k, 0) << 16) | 0xFF000000u;
+            for (int k = 0; k < PX; k++) e[k] = __byte_perm(pixel(k), 0xFFu, 0x4012);
             if (VEC && PX % 4 == 0 && rgba_vec && nv == PX) {
 #pragma unroll
                 for (int q = 0; q < PX / 4; q++) reinterpret_cast<uint4*>(o)[q] = make_uint4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
@@ -204,7 +222,7 @@ constexpr int CM_QG = 8 * CM_BW;    // 4-pixel column groups per threshold row (
 constexpr int CM_QN = (8 + CM_TW + 5 + 3) / 4;   // groups that hold a column some output pixel reads (68)
 constexpr int CM_SEG = 11;          // threshold rows per row segment
 static_assert(CM_NT == 4 * CM_QG && 4 * CM_SEG >= CM_BH, "thread = (column group, one of 4 row segments)");
-static_assert(2 + CM_QN < CM_GW / 4, "the last group's right neighbour word lies inside the gray tile");
+static_assert(2 + CM_QN - 1 + 1 < CM_GW / 4, "the last group's right neighbour word lies inside the gray tile");
 
 __global__ void __launch_bounds__(CM_NT) contrast_mask_kernel(const uint8_t* __restrict__ gray, int w, int h, int stride,
                                                               uint8_t* __restrict__ mask, int mask_stride)
@@ -242,46 +260,47 @@ __global__ void __launch_bounds__(CM_NT) contrast_mask_kernel(const uint8_t* __r
     //     share a register as 16-bit lanes, so the vertical pass is three integer operations per pixel PAIR
     //     (minuend and subtrahend are sums of positives: no borrow crosses the lanes), and the constant puts
     //     `s >= 21` into bit 15 of each lane.  The four bits of a thread and the nibbles of eight adjacent
-    //     threads (redux.or) make one word of the threshold bit-plane.
+    //     threads (xor-butterfly) make one word of the threshold bit-plane.
     {
         const uint32_t* Gw = reinterpret_cast<const uint32_t*>(&G[0][0]);
         constexpr int GWW = CM_GW / 4;                  // words per gray row
         const int q = tid % CM_QG, seg = tid / CM_QG;
-        const bool q_ok = q < CM_QN;                    // groups beyond the last needed column read nothing
-        const int wq = 2 + q;                           // word of the group's first pixel (column t0-8+4q) in a gray row
+        // word of the group's first pixel (column t0-8+4q) in a gray row.  Groups past the last column that any
+        // output pixel reads (q >= CM_QN) are clamped into the tile: their bits (>= 272) are never looked at.
+        const int wq = 2 + min(q, CM_QN - 1);
         const int X0 = t0 - 8 + 4 * q;
-        uint32_t colmask = 0;
+        uint32_t colmask = 0;   // out-of-frame columns must stay 0: step (3) ORs their reflections in
 #pragma unroll
         for (int j = 0; j < 4; j++) colmask |= (uint32_t)(X0 + j >= 0 && X0 + j < w) << j;
         const int tr0 = CM_SEG * seg;
-        const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
+        const uint32_t* gcol = Gw + wq;
+        const bool writer = (tid & 7) == 0;
         uint32_t p[5][2];                               // packed horizontal derivatives of gray rows gr-4 .. gr
 #pragma unroll
         for (int it = 0; it < CM_SEG + 4; it++) {
-            const int gr = tr0 + it;                    // gray row of this iteration
+            const int gr = min(tr0 + it, CM_GH - 1);    // gray row of this iteration (rows past the tile only feed unused threshold rows)
 #pragma unroll
             for (int k = 0; k < 4; k++) { p[k][0] = p[k + 1][0]; p[k][1] = p[k + 1][1]; }
-            uint32_t W0 = 0, W1 = 0, W2 = 0;
-            if (q_ok && gr < CM_GH) {
-                const uint32_t* gw_ = Gw + gr * GWW + wq;
-                W0 = gw_[-1]; W1 = gw_[0]; W2 = gw_[1];
-            }
+            const uint32_t* gw_ = gcol + gr * GWW;
+            const uint32_t W0 = gw_[-1], W1 = gw_[0], W2 = gw_[1];
             const int h0 = dp4a_us(W1, 0x00010000, dp4a_us(__funnelshift_r(W0, W1, 16), 0x0200FEFF, 1024));
             const int h1 = dp4a_us(W1, 0x01000000, dp4a_us(__funnelshift_r(W0, W1, 24), 0x0200FEFF, 1024));
             const int h2 = dp4a_us(W2, 0x00000001, dp4a_us(W1, 0x0200FEFF, 1024));
             const int h3 = dp4a_us(W2, 0x00000100, dp4a_us(__funnelshift_r(W1, W2, 8), 0x0200FEFF, 1024));
-            p[4][0] = (uint32_t)h1 * 65536u + (uint32_t)h0;
-            p[4][1] = (uint32_t)h3 * 65536u + (uint32_t)h2;
-            if (it >= 4) {                              // centre = gray row gr-2 = threshold row gr-4
-                const int tr = gr - 4, py = ty0 - 5 + tr;
-                // lane = s + 32747, s = h[gr] - h[gr-4] + 2 (h[gr-1] - h[gr-3]): bit 15 <=> s > 20
+            p[4][0] = __byte_perm((uint32_t)h0, (uint32_t)h1, 0x5410);
+            p[4][1] = __byte_perm((uint32_t)h2, (uint32_t)h3, 0x5410);
+            if (it >= 4) {                              // centre = gray row gr-2 = threshold row tr (frame row ty0-5+tr)
+                const int tr = tr0 + it - 4;
+                // lane = s + 32747, s = h[gr] - h[gr-4] + 2 (h[gr-1] - h[gr-3]): bit 15 <=> s > 20.  Rows outside the
+                // frame need no masking: step (4) reflects row indices and never reads them.
                 const uint32_t slo = (p[4][0] + 2u * p[3][0] + 0x7FEB7FEBu) - (p[0][0] + 2u * p[1][0]);
                 const uint32_t shi = (p[4][1] + 2u * p[3][1] + 0x7FEB7FEBu) - (p[0][1] + 2u * p[1][1]);
                 const uint32_t v = ((slo >> 15) & 0x10001u) | (((shi >> 15) & 0x10001u) << 2);
-                uint32_t nib = (v | (v >> 15)) & colmask;
-                if (py < 0 || py >= h) nib = 0u;
-                const uint32_t word = __reduce_or_sync(gmask, nib << (4 * (tid & 7)));
-                if ((tid & 7) == 0 && tr < CM_BH) T[tr][q >> 3] = word;
+                uint32_t word = ((v | (v >> 15)) & colmask) << (4 * (tid & 7));   // OR over the 8 lanes of the group
+                word |= __shfl_xor_sync(0xffffffffu, word, 1);
+                word |= __shfl_xor_sync(0xffffffffu, word, 2);
+                word |= __shfl_xor_sync(0xffffffffu, word, 4);
+                if (writer && tr < CM_BH) T[tr][q >> 3] = word;
             }
         }
     }
@@ -362,26 +381,28 @@ __device__ __forceinline__ int cell_start(int c, int len, float inv, float gm1)
 }
 
 constexpr float F32_EPSILON = 1.1920928955078125e-07f;
-constexpr int FC_NT = 128;        // threads per CTA: all of them issue the copies, warp 0 folds
-constexpr int FC_NC = 32;         // cells per CTA (adjacent cells of one cell row), one lane each
-constexpr int FC_CAP = 2048;      // pixels per staging buffer (16 KB of flow)
-constexpr int FC_MCAP = 4096;     // mask bytes per staging buffer
+constexpr int FC_NT = 128;        // threads per CTA: warp 0 folds, warps 1-3 keep the copies in flight
+constexpr int FC_NC = 32;         // cells per CTA (adjacent cells of one cell row), one lane of warp 0 each
+constexpr int FC_NST = 4;         // staging buffers (ring): three steps in flight while one is folded
+constexpr int FC_CAP = 1024;      // pixels per staging buffer (8 KB of flow)
+constexpr int FC_MCAP = 2048;     // mask bytes per staging buffer
 
-struct CellRec { float mx, my; uint32_t touched, pad; };
+struct __align__(16) CellRec { float mx, my; uint32_t touched, pad; };
 
-// One CTA = FC_NC adjacent cells of one cell row.  Their pixel rectangle is streamed through two shared-memory
-// buffers: while warp 0 folds the rows of one buffer, the copies of the next step are already in flight
-// (ASYNC: 16-byte asynchronous copies, two flow pixels / sixteen mask bytes each, starting at the aligned
-// address below the first pixel).  Lane t folds the pixels of cell t in raster order — rows top to bottom,
-// columns left to right — which is the order in which the reference's loop reaches that cell, so sums and counts
-// are bit-identical:  counts += 1.0 (from f32::EPSILON), sum = motion * 1.0 + sum, motion = flow .* (1/W, 1/H).
+// One CTA = FC_NC adjacent cells of one cell row.  Their pixel rectangle is streamed through a ring of FC_NST
+// shared-memory buffers: warps 1-3 issue the copies of step s+3 (ASYNC: 16-byte asynchronous copies, two flow
+// pixels / sixteen mask bytes each, starting at the aligned address below the first pixel) while warp 0 folds
+// step s, so the sequential fold never waits for HBM in steady state and ~3 steps per CTA are in flight.
+// Lane t folds the pixels of cell t in raster order — rows top to bottom, columns left to right — which is the
+// order in which the reference's loop reaches that cell, so sums and counts are bit-identical:
+//   counts += 1.0 (from f32::EPSILON), sum = motion * 1.0 + sum, motion = flow .* (1/W, 1/H).
 template <bool ASYNC>
 __global__ void __launch_bounds__(FC_NT) flow_cells_kernel(const float* __restrict__ flow, long long flow_stride,
                                                            const uint8_t* __restrict__ mask, long long mask_stride,
                                                            int w, int h, int gw, int gh, CellRec* __restrict__ cells)
 {
-    __shared__ __align__(16) float2 sflow[2][FC_CAP];
-    __shared__ __align__(16) uint8_t smask[2][FC_MCAP];
+    __shared__ __align__(16) float2 sflow[FC_NST][FC_CAP];
+    __shared__ __align__(16) uint8_t smask[FC_NST][FC_MCAP];
     __shared__ int sxs[FC_NC + 1], sys_[2];
     const int tid = threadIdx.x;
     const int cy = blockIdx.y, c0 = blockIdx.x * FC_NC, c1 = min(c0 + FC_NC, gw);
@@ -402,69 +423,80 @@ __global__ void __launch_bounds__(FC_NT) flow_cells_kernel(const float* __restri
         const int pitchm = (cw + 30) & ~15;            // row pitch of the mask buffer (bytes; multiple of 16, >= cw + 15)
         const int rg = max(1, min(FC_CAP / pitchf, FC_MCAP / pitchm));   // rows per step; > 1 only when cw == span
         const int ncs = (span + cw - 1) / cw, nrs = (rows + rg - 1) / rg, nsteps = ncs * nrs;
-        auto stage = [&](int s) {   // issue the copies of step s into buffer s & 1
-            const int ri = s / ncs, ci = s - ri * ncs;
-            const int r0 = y0 + ri * rg, nr = min(rg, y1 - r0);
-            const int cx0 = px0 + ci * cw, nc = min(cw, px1 - cx0);
-            float2* sf = sflow[s & 1];
-            uint8_t* sm = smask[s & 1];
-            if (ASYNC) {
-                const int ax0 = cx0 & ~1, nf = (cx0 + nc - ax0 + 1) >> 1;
-                for (int r = 0; r < nr; r++) {
-                    const float* frow = flow + (long long)(r0 + r) * flow_stride + 2ll * ax0;
-                    for (int k = tid; k < nf; k += FC_NT) async_copy16(sf + r * pitchf + 2 * k, frow + 4 * k);
-                }
-                if (mask) {
-                    const int am0 = cx0 & ~15, nm = (cx0 + nc - am0 + 15) >> 4;
+        const int ptid = tid - 32;                     // producer index (warps 1-3)
+        constexpr int NP = FC_NT - 32;
+        auto stage = [&](int s) {   // producers issue the copies of step s into buffer s % FC_NST; everybody commits
+            if (s < nsteps && ptid >= 0) {
+                const int ri = s / ncs, ci = s - ri * ncs;
+                const int r0 = y0 + ri * rg, nr = min(rg, y1 - r0);
+                const int cx0 = px0 + ci * cw, nc = min(cw, px1 - cx0);
+                float2* sf = sflow[s % FC_NST];
+                uint8_t* sm = smask[s % FC_NST];
+                if (ASYNC) {
+                    const int ax0 = cx0 & ~1, nf = (cx0 + nc - ax0 + 1) >> 1;
                     for (int r = 0; r < nr; r++) {
-                        const uint8_t* mrow = mask + (long long)(r0 + r) * mask_stride + am0;
-                        for (int k = tid; k < nm; k += FC_NT) async_copy16(sm + r * pitchm + 16 * k, mrow + 16 * k);
+                        const float* frow = flow + (long long)(r0 + r) * flow_stride + 2ll * ax0;
+                        float2* srow = sf + r * pitchf;
+                        for (int k = ptid; k < nf; k += NP) async_copy16(srow + 2 * k, frow + 4 * k);
                     }
-                }
-            } else {
-                for (int r = 0; r < nr; r++) {
-                    const float* frow = flow + (long long)(r0 + r) * flow_stride + 2ll * cx0;
-                    for (int c = tid; c < nc; c += FC_NT) sf[r * pitchf + c] = make_float2(__ldg(frow + 2 * c), __ldg(frow + 2 * c + 1));
                     if (mask) {
-                        const uint8_t* mrow = mask + (long long)(r0 + r) * mask_stride + cx0;
-                        for (int c = tid; c < nc; c += FC_NT) sm[r * pitchm + c] = __ldg(mrow + c);
+                        const int am0 = cx0 & ~15, nm = (cx0 + nc - am0 + 15) >> 4;
+                        for (int r = 0; r < nr; r++) {
+                            const uint8_t* mrow = mask + (long long)(r0 + r) * mask_stride + am0;
+                            for (int k = ptid; k < nm; k += NP) async_copy16(sm + r * pitchm + 16 * k, mrow + 16 * k);
+                        }
+                    }
+                } else {
+                    for (int r = 0; r < nr; r++) {
+                        const float* frow = flow + (long long)(r0 + r) * flow_stride + 2ll * cx0;
+                        for (int c = ptid; c < nc; c += NP) sf[r * pitchf + c] = make_float2(__ldg(frow + 2 * c), __ldg(frow + 2 * c + 1));
+                        if (mask) {
+                            const uint8_t* mrow = mask + (long long)(r0 + r) * mask_stride + cx0;
+                            for (int c = ptid; c < nc; c += NP) sm[r * pitchm + c] = __ldg(mrow + c);
+                        }
                     }
                 }
             }
-            async_copy_commit();
+            async_copy_commit();   // one group per call and thread (possibly empty) keeps wait_group's count uniform
         };
-        stage(0);
+#pragma unroll
+        for (int s = 0; s < FC_NST - 1; s++) stage(s);
         for (int s = 0; s < nsteps; s++) {
-            if (s + 1 < nsteps) {
-                stage(s + 1);
-                async_copy_wait<1>();   // everything but the copies just issued has landed
-            } else {
-                async_copy_wait<0>();
-            }
-            __syncthreads();
+            stage(s + FC_NST - 1);                 // into the buffer folded in the previous iteration
+            async_copy_wait<FC_NST - 1>();         // this thread's copies of step s have landed
+            __syncthreads();                       // ... and everybody else's
             if (owner) {
                 const int ri = s / ncs, ci = s - ri * ncs;
                 const int r0 = y0 + ri * rg, nr = min(rg, y1 - r0);
                 const int cx0 = px0 + ci * cw, nc = min(cw, px1 - cx0);
                 const int a = max(xa, cx0) - cx0, b = min(xb, cx0 + nc) - cx0;
-                const float2* sf = sflow[s & 1] + (ASYNC ? (cx0 & 1) : 0);
-                const uint8_t* sm = smask[s & 1] + (ASYNC ? (cx0 & 15) : 0);
+                const float2* sf = sflow[s % FC_NST] + (ASYNC ? (cx0 & 1) : 0);
+                const uint8_t* sm = smask[s % FC_NST] + (ASYNC ? (cx0 & 15) : 0);
                 for (int r = 0; r < nr; r++) {
                     const float2* fr = sf + r * pitchf;
                     const uint8_t* mr = sm + r * pitchm;
+                    if (mask) {
 #pragma unroll 4
-                    for (int c = a; c < b; c++) {
-                        const bool keep = !mask || mr[c] != 0;   // `*mask < 0.1` -> skip (cv-decoder:258)
-                        const float2 f = fr[c];
-                        const float ncnt = __fadd_rn(cnt, 1.0f);
-                        const float nsx = __fadd_rn(__fmul_rn(f.x, nx), sx), nsy = __fadd_rn(__fmul_rn(f.y, ny), sy);
-                        cnt = keep ? ncnt : cnt;
-                        sx = keep ? nsx : sx;
-                        sy = keep ? nsy : sy;
+                        for (int c = a; c < b; c++) {
+                            const float2 f = fr[c];
+                            if (mr[c] != 0) {   // `*mask < 0.1` -> skip (cv-decoder:258)
+                                cnt = __fadd_rn(cnt, 1.0f);
+                                sx = __fadd_rn(__fmul_rn(f.x, nx), sx);
+                                sy = __fadd_rn(__fmul_rn(f.y, ny), sy);
+                            }
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int c = a; c < b; c++) {
+                            const float2 f = fr[c];
+                            cnt = __fadd_rn(cnt, 1.0f);
+                            sx = __fadd_rn(__fmul_rn(f.x, nx), sx);
+                            sy = __fadd_rn(__fmul_rn(f.y, ny), sy);
+                        }
                     }
                 }
             }
-            __syncthreads();   // buffer s & 1 is free for the copies of step s + 2
+            __syncthreads();   // buffer s % FC_NST is free for the copies of step s + FC_NST
         }
     }
     if (owner) {
@@ -515,13 +547,16 @@ __global__ void __launch_bounds__(1024) flow_emit_cells_kernel(const CellRec* __
     for (long long k0 = 0; k0 < total; k0 += (long long)blockDim.x * FE_PER) {
         const long long kb = k0 + (long long)threadIdx.x * FE_PER;
         uint32_t flags = 0;
+        uint4 rec[FE_PER];   // the records stay in registers: the ordered writes below need no second load
 #pragma unroll
         for (int j = 0; j < FE_PER; j++) {
             const long long k = kb + j;
+            rec[j] = make_uint4(0u, 0u, 0u, 0u);
             if (k < total) {
                 const int x = (int)(k / gh), y = (int)(k - (long long)x * gh);
-                flags |= (cells[(size_t)y * gw + x].touched & 1u) << j;
+                rec[j] = __ldg(reinterpret_cast<const uint4*>(cells) + ((size_t)y * gw + x));
             }
+            flags |= (rec[j].z & 1u) << j;
         }
         uint32_t tot;
         unsigned long long pos = base + block_excl_scan(__popc(flags), warp_tot, &tot);
@@ -531,12 +566,11 @@ __global__ void __launch_bounds__(1024) flow_emit_cells_kernel(const CellRec* __
                 const long long k = kb + j;
                 const int x = (int)(k / gh), y = (int)(k - (long long)x * gh);
                 if (pos < cap) {
-                    const CellRec rec = cells[(size_t)y * gw + x];
                     ofps_mv e;
                     e.px = __fmul_rn(__fadd_rn((float)x, 0.5f), gx);
                     e.py = __fmul_rn(__fadd_rn((float)y, 0.5f), gy);
-                    e.mx = rec.mx;
-                    e.my = rec.my;
+                    e.mx = __uint_as_float(rec[j].x);
+                    e.my = __uint_as_float(rec[j].y);
                     out[pos] = e;
                 }
                 pos++;
@@ -644,13 +678,13 @@ int launch_frame_convert(const uint8_t* d_src, int w, int h, int stride, int cha
     const int rgba_vec = d_rgba && (reinterpret_cast<uintptr_t>(d_rgba) & 15u) == 0 && (w & 3) == 0;
     uint32_t* rgba = reinterpret_cast<uint32_t*>(d_rgba);
     const int px = vec ? 16 : 4;
-    const dim3 grid((unsigned)(((w + px - 1) / px + 255) / 256), (unsigned)(h < 65535 ? h : 65535));
+    const dim3 grid((unsigned)(((w + px - 1) / px + 127) / 128), (unsigned)(h < 65535 ? h : 65535));   // small CTAs: even waves
     if (channels == 3) {
-        if (vec) OFPSB_LAUNCH((frame_convert_kernel<3, 16, true>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
-        else OFPSB_LAUNCH((frame_convert_kernel<3, 4, false>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
+        if (vec) OFPSB_LAUNCH((frame_convert_kernel<3, 16, true>), grid, 128, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
+        else OFPSB_LAUNCH((frame_convert_kernel<3, 4, false>), grid, 128, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
     } else {
-        if (vec) OFPSB_LAUNCH((frame_convert_kernel<4, 16, true>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
-        else OFPSB_LAUNCH((frame_convert_kernel<4, 4, false>), grid, 256, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
+        if (vec) OFPSB_LAUNCH((frame_convert_kernel<4, 16, true>), grid, 128, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
+        else OFPSB_LAUNCH((frame_convert_kernel<4, 4, false>), grid, 128, stream, d_src, w, h, stride, rgb_order, d_gray, gray_stride, rgba, rgba_vec);
     }
     OFPSB_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 1;

@@ -101,6 +101,13 @@ inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned d)
     const unsigned lane = emu::t_linear & 31;
     return lane >= d ? t[lane - d] : v;
 }
+inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, unsigned m)
+{
+    uint32_t t[32];
+    emu_exchange(v, t);
+    return t[(emu::t_linear & 31) ^ m];
+}
+inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline uint32_t __reduce_add_sync(unsigned, uint32_t v)
 {
     uint32_t t[32], s = 0;
@@ -132,6 +139,13 @@ inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline int __float2int_rn(float a) { return (int)lrintf(a); }
+inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel)
+{
+    const unsigned long long v = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 255u) << (8 * i);
+    return r;
+}
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((unsigned long long)hi << 32) | lo) >> (sh & 31)); }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
