@@ -7,6 +7,11 @@
 #include <cuda_runtime.h>
 // Kernel launch on `stream` without dynamic shared memory; the emulation build redefines it.
 #define OFPSB_LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#define OFPSB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+// the kernel's dynamic shared memory as a byte array
+#define OFPSB_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+// keeps the compiler from sinking already-issued loads under a later predicate
+#define OFPSB_KEEP_LOADED(a, b) asm volatile("" : "+f"(a), "+f"(b))
 #endif
 #include <cstdarg>
 #include <cstdint>

@@ -381,40 +381,38 @@ __device__ __forceinline__ int cell_start(int c, int len, float inv, float gm1)
 }
 
 constexpr float F32_EPSILON = 1.1920928955078125e-07f;
-constexpr int FC_NT = 128;        // threads per CTA: warp 0 folds, warps 1-3 keep the copies in flight
-constexpr int FC_NC = 32;         // cells per CTA (adjacent cells of one cell row), one lane of warp 0 each
-constexpr int FC_NST = 4;         // staging buffers (ring): three steps in flight while one is folded
-constexpr int FC_CAP = 1024;      // pixels per staging buffer (8 KB of flow)
-constexpr int FC_MCAP = 2048;     // mask bytes per staging buffer
+constexpr int FC_NC = 32;         // cells per CTA = one warp: adjacent cells of one cell row, one lane each
+constexpr int FC_NST = 3;         // staging buffers (ring): two steps in flight while one is folded
+constexpr int FC_CAP = 2048;      // pixels per staging buffer (16 KB of flow)
+constexpr int FC_MCAP = 2112;     // mask bytes per staging buffer (>= FC_CAP + 30, multiple of 16)
+constexpr int FC_STAGE_BYTES = FC_CAP * 8 + FC_MCAP;
+constexpr int FC_SMEM_BYTES = FC_NST * FC_STAGE_BYTES;   // 55,488 B of dynamic shared memory: 4 CTAs per SM
 
 struct __align__(16) CellRec { float mx, my; uint32_t touched, pad; };
 
-// One CTA = FC_NC adjacent cells of one cell row.  Their pixel rectangle is streamed through a ring of FC_NST
-// shared-memory buffers: warps 1-3 issue the copies of step s+3 (ASYNC: 16-byte asynchronous copies, two flow
-// pixels / sixteen mask bytes each, starting at the aligned address below the first pixel) while warp 0 folds
-// step s, so the sequential fold never waits for HBM in steady state and ~3 steps per CTA are in flight.
+// One CTA = ONE WARP = FC_NC adjacent cells of one cell row; no block-wide barrier anywhere.  The warp streams the
+// pixel rows of its cells through a ring of FC_NST shared-memory buffers: it issues the copies of step s+2
+// (ASYNC: 16-byte asynchronous copies, two flow pixels / sixteen mask bytes each, starting at the aligned address
+// below the first pixel), then folds step s while they are in flight.  (Measured alternatives: a 4-warp CTA with
+// one folding warp spends its time in __syncthreads hand-offs — 41 us at 4K against 16 us here.)
 // Lane t folds the pixels of cell t in raster order — rows top to bottom, columns left to right — which is the
 // order in which the reference's loop reaches that cell, so sums and counts are bit-identical:
 //   counts += 1.0 (from f32::EPSILON), sum = motion * 1.0 + sum, motion = flow .* (1/W, 1/H).
 template <bool ASYNC>
-__global__ void __launch_bounds__(FC_NT) flow_cells_kernel(const float* __restrict__ flow, long long flow_stride,
-                                                           const uint8_t* __restrict__ mask, long long mask_stride,
-                                                           int w, int h, int gw, int gh, CellRec* __restrict__ cells)
+__global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict__ flow, long long flow_stride,
+                                                        const uint8_t* __restrict__ mask, long long mask_stride,
+                                                        int w, int h, int gw, int gh, CellRec* __restrict__ cells)
 {
-    __shared__ __align__(16) float2 sflow[FC_NST][FC_CAP];
-    __shared__ __align__(16) uint8_t smask[FC_NST][FC_MCAP];
-    __shared__ int sxs[FC_NC + 1], sys_[2];
-    const int tid = threadIdx.x;
-    const int cy = blockIdx.y, c0 = blockIdx.x * FC_NC, c1 = min(c0 + FC_NC, gw);
+    OFPSB_DYN_SMEM(dyn);
+    const int lane = threadIdx.x;
+    const int cy = blockIdx.y, c0 = blockIdx.x * FC_NC;
     const float nx = __fdiv_rn(1.0f, (float)w), ny = __fdiv_rn(1.0f, (float)h);
-    if (tid <= FC_NC) sxs[tid] = cell_start(min(c0 + tid, gw), w, nx, (float)(gw - 1));
-    else if (tid < FC_NC + 3) sys_[tid - FC_NC - 1] = cell_start(cy + tid - FC_NC - 1, h, ny, (float)(gh - 1));
-    __syncthreads();
-    const int y0 = sys_[0], y1 = sys_[1];
-    const int px0 = sxs[0], px1 = sxs[c1 - c0];
-    const int cell = c0 + tid;
-    const bool owner = tid < FC_NC && cell < c1;
-    const int xa = owner ? sxs[tid] : 0, xb = owner ? sxs[tid + 1] : 0;
+    const float gxm1 = (float)(gw - 1), gym1 = (float)(gh - 1);
+    const int cell = c0 + lane;
+    const bool owner = cell < gw;
+    const int xa = cell_start(min(cell, gw), w, nx, gxm1), xb = cell_start(min(cell + 1, gw), w, nx, gxm1);
+    const int px0 = __shfl_sync(0xffffffffu, xa, 0), px1 = __shfl_sync(0xffffffffu, xb, 31);
+    const int y0 = cell_start(cy, h, ny, gym1), y1 = cell_start(cy + 1, h, ny, gym1);
     float sx = 0.0f, sy = 0.0f, cnt = F32_EPSILON;
     const int span = px1 - px0, rows = y1 - y0;
     if (span > 0 && rows > 0) {
@@ -423,63 +421,63 @@ __global__ void __launch_bounds__(FC_NT) flow_cells_kernel(const float* __restri
         const int pitchm = (cw + 30) & ~15;            // row pitch of the mask buffer (bytes; multiple of 16, >= cw + 15)
         const int rg = max(1, min(FC_CAP / pitchf, FC_MCAP / pitchm));   // rows per step; > 1 only when cw == span
         const int ncs = (span + cw - 1) / cw, nrs = (rows + rg - 1) / rg, nsteps = ncs * nrs;
-        const int ptid = tid - 32;                     // producer index (warps 1-3)
-        constexpr int NP = FC_NT - 32;
-        auto stage = [&](int s) {   // producers issue the copies of step s into buffer s % FC_NST; everybody commits
-            if (s < nsteps && ptid >= 0) {
+        auto stage = [&](int s) {   // issue the copies of step s into buffer s % FC_NST, commit one group
+            if (s < nsteps) {
                 const int ri = s / ncs, ci = s - ri * ncs;
                 const int r0 = y0 + ri * rg, nr = min(rg, y1 - r0);
                 const int cx0 = px0 + ci * cw, nc = min(cw, px1 - cx0);
-                float2* sf = sflow[s % FC_NST];
-                uint8_t* sm = smask[s % FC_NST];
+                float2* sf = reinterpret_cast<float2*>(dyn + (s % FC_NST) * FC_STAGE_BYTES);
+                uint8_t* sm = dyn + (s % FC_NST) * FC_STAGE_BYTES + FC_CAP * 8;
                 if (ASYNC) {
                     const int ax0 = cx0 & ~1, nf = (cx0 + nc - ax0 + 1) >> 1;
                     for (int r = 0; r < nr; r++) {
                         const float* frow = flow + (long long)(r0 + r) * flow_stride + 2ll * ax0;
                         float2* srow = sf + r * pitchf;
-                        for (int k = ptid; k < nf; k += NP) async_copy16(srow + 2 * k, frow + 4 * k);
+                        for (int k = lane; k < nf; k += 32) async_copy16(srow + 2 * k, frow + 4 * k);
                     }
                     if (mask) {
                         const int am0 = cx0 & ~15, nm = (cx0 + nc - am0 + 15) >> 4;
                         for (int r = 0; r < nr; r++) {
                             const uint8_t* mrow = mask + (long long)(r0 + r) * mask_stride + am0;
-                            for (int k = ptid; k < nm; k += NP) async_copy16(sm + r * pitchm + 16 * k, mrow + 16 * k);
+                            for (int k = lane; k < nm; k += 32) async_copy16(sm + r * pitchm + 16 * k, mrow + 16 * k);
                         }
                     }
                 } else {
                     for (int r = 0; r < nr; r++) {
                         const float* frow = flow + (long long)(r0 + r) * flow_stride + 2ll * cx0;
-                        for (int c = ptid; c < nc; c += NP) sf[r * pitchf + c] = make_float2(__ldg(frow + 2 * c), __ldg(frow + 2 * c + 1));
+                        for (int c = lane; c < nc; c += 32) sf[r * pitchf + c] = make_float2(__ldg(frow + 2 * c), __ldg(frow + 2 * c + 1));
                         if (mask) {
                             const uint8_t* mrow = mask + (long long)(r0 + r) * mask_stride + cx0;
-                            for (int c = ptid; c < nc; c += NP) sm[r * pitchm + c] = __ldg(mrow + c);
+                            for (int c = lane; c < nc; c += 32) sm[r * pitchm + c] = __ldg(mrow + c);
                         }
                     }
                 }
             }
-            async_copy_commit();   // one group per call and thread (possibly empty) keeps wait_group's count uniform
+            async_copy_commit();   // one group per call (possibly empty) keeps wait_group's count uniform
         };
 #pragma unroll
         for (int s = 0; s < FC_NST - 1; s++) stage(s);
         for (int s = 0; s < nsteps; s++) {
             stage(s + FC_NST - 1);                 // into the buffer folded in the previous iteration
-            async_copy_wait<FC_NST - 1>();         // this thread's copies of step s have landed
-            __syncthreads();                       // ... and everybody else's
+            async_copy_wait<FC_NST - 1>();         // this lane's copies of step s have landed
+            __syncwarp();                          // ... and the other lanes' too
             if (owner) {
                 const int ri = s / ncs, ci = s - ri * ncs;
                 const int r0 = y0 + ri * rg, nr = min(rg, y1 - r0);
                 const int cx0 = px0 + ci * cw, nc = min(cw, px1 - cx0);
                 const int a = max(xa, cx0) - cx0, b = min(xb, cx0 + nc) - cx0;
-                const float2* sf = sflow[s % FC_NST] + (ASYNC ? (cx0 & 1) : 0);
-                const uint8_t* sm = smask[s % FC_NST] + (ASYNC ? (cx0 & 15) : 0);
+                const float2* sf = reinterpret_cast<const float2*>(dyn + (s % FC_NST) * FC_STAGE_BYTES) + (ASYNC ? (cx0 & 1) : 0);
+                const uint8_t* sm = dyn + (s % FC_NST) * FC_STAGE_BYTES + FC_CAP * 8 + (ASYNC ? (cx0 & 15) : 0);
                 for (int r = 0; r < nr; r++) {
                     const float2* fr = sf + r * pitchf;
                     const uint8_t* mr = sm + r * pitchm;
                     if (mask) {
 #pragma unroll 4
                         for (int c = a; c < b; c++) {
-                            const float2 f = fr[c];
-                            if (mr[c] != 0) {   // `*mask < 0.1` -> skip (cv-decoder:258)
+                            float2 f = fr[c];
+                            const bool keep = mr[c] != 0;   // `*mask < 0.1` -> skip (cv-decoder:258)
+                            OFPSB_KEEP_LOADED(f.x, f.y);    // the flow load must not wait for the mask byte
+                            if (keep) {
                                 cnt = __fadd_rn(cnt, 1.0f);
                                 sx = __fadd_rn(__fmul_rn(f.x, nx), sx);
                                 sy = __fadd_rn(__fmul_rn(f.y, ny), sy);
@@ -496,7 +494,7 @@ __global__ void __launch_bounds__(FC_NT) flow_cells_kernel(const float* __restri
                     }
                 }
             }
-            __syncthreads();   // buffer s % FC_NST is free for the copies of step s + FC_NST
+            __syncwarp();   // buffer s % FC_NST is free for the copies of step s + FC_NST
         }
     }
     if (owner) {
@@ -784,12 +782,23 @@ int launch_flow_entries(const float* d_flow, size_t flow_stride, const uint8_t* 
     // 16-byte asynchronous staging needs 16-byte aligned flow rows (and mask rows, when there is a mask)
     const bool async = ((reinterpret_cast<uintptr_t>(d_flow) & 15u) | (flow_stride & 3u)) == 0 &&
                        (!d_mask || ((reinterpret_cast<uintptr_t>(d_mask) & 15u) | (mask_stride & 15u)) == 0);
+#ifndef OFPSB_EMU
+    static bool smem_opt_in_dev[64] = {};   // > 48 KB of dynamic shared memory needs the opt-in, once per device and kernel
+    int dev = 0;
+    OFPSB_CUDA_TRY(cudaGetDevice(&dev));
+    bool& smem_opt_in = smem_opt_in_dev[dev & 63];
+    if (!smem_opt_in) {
+        OFPSB_CUDA_TRY(cudaFuncSetAttribute(flow_cells_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
+        OFPSB_CUDA_TRY(cudaFuncSetAttribute(flow_cells_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
+        smem_opt_in = true;
+    }
+#endif
     if (async)
-        OFPSB_LAUNCH(flow_cells_kernel<true>, grid, FC_NT, stream, d_flow, (long long)flow_stride, d_mask, (long long)mask_stride, w,
-                     h, igw, igh, cells);
+        OFPSB_LAUNCH_SMEM(flow_cells_kernel<true>, grid, 32, FC_SMEM_BYTES, stream, d_flow, (long long)flow_stride, d_mask,
+                          (long long)mask_stride, w, h, igw, igh, cells);
     else
-        OFPSB_LAUNCH(flow_cells_kernel<false>, grid, FC_NT, stream, d_flow, (long long)flow_stride, d_mask, (long long)mask_stride, w,
-                     h, igw, igh, cells);
+        OFPSB_LAUNCH_SMEM(flow_cells_kernel<false>, grid, 32, FC_SMEM_BYTES, stream, d_flow, (long long)flow_stride, d_mask,
+                          (long long)mask_stride, w, h, igw, igh, cells);
     OFPSB_LAUNCH(flow_emit_cells_kernel, 1, 1024, stream, cells, igw, igh, d_entries, cap, d_count);
     OFPSB_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 2;

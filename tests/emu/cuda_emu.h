@@ -101,6 +101,12 @@ inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned d)
     const unsigned lane = emu::t_linear & 31;
     return lane >= d ? t[lane - d] : v;
 }
+inline int __shfl_sync(unsigned, int v, int src)
+{
+    uint32_t t[32];
+    emu_exchange((uint32_t)v, t);
+    return (int)t[src & 31];
+}
 inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, unsigned m)
 {
     uint32_t t[32];
@@ -179,4 +185,7 @@ template <typename F> void launch(dim3 grid, dim3 block, F body)
 }
 }  // namespace emu
 
+#define OFPSB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) ::emu::launch(dim3(grid), dim3(block), [=] { kernel(__VA_ARGS__); })
+#define OFPSB_DYN_SMEM(name) static __attribute__((aligned(16))) uint8_t name[232448]
+#define OFPSB_KEEP_LOADED(a, b) ((void)0)
 #define OFPSB_LAUNCH(kernel, grid, block, stream, ...) ::emu::launch(dim3(grid), dim3(block), [=] { kernel(__VA_ARGS__); })
