@@ -382,18 +382,19 @@ __device__ __forceinline__ int cell_start(int c, int len, float inv, float gm1)
 
 constexpr float F32_EPSILON = 1.1920928955078125e-07f;
 constexpr int FC_NC = 32;         // cells per CTA = one warp: adjacent cells of one cell row, one lane each
-constexpr int FC_NST = 3;         // staging buffers (ring): two steps in flight while one is folded
-constexpr int FC_CAP = 2048;      // pixels per staging buffer (16 KB of flow)
-constexpr int FC_MCAP = 2112;     // mask bytes per staging buffer (>= FC_CAP + 30, multiple of 16)
-constexpr int FC_STAGE_BYTES = FC_CAP * 8 + FC_MCAP;
-constexpr int FC_SMEM_BYTES = FC_NST * FC_STAGE_BYTES;   // 55,488 B of dynamic shared memory: 4 CTAs per SM
+constexpr int FC_CAP = 2048;      // most pixels of one row in a step (wider spans are walked in chunks)
+constexpr int FC_STEP_PX = 1024;  // rows are grouped into steps of about this many pixels
+constexpr int FC_MAX_NST = 8;     // most staging buffers in the ring
+constexpr int FC_SMEM_BYTES = 72 * 1024;   // dynamic shared memory per CTA (3 CTAs per SM): the ring takes as many
+                                           // buffers of the step's size as fit, at least 3 (FC_CAP * 8 + mask < 24 KB)
 
 struct __align__(16) CellRec { float mx, my; uint32_t touched, pad; };
 
 // One CTA = ONE WARP = FC_NC adjacent cells of one cell row; no block-wide barrier anywhere.  The warp streams the
-// pixel rows of its cells through a ring of FC_NST shared-memory buffers: it issues the copies of step s+2
-// (ASYNC: 16-byte asynchronous copies, two flow pixels / sixteen mask bytes each, starting at the aligned address
-// below the first pixel), then folds step s while they are in flight.  (Measured alternatives: a 4-warp CTA with
+// pixel rows of its cells through a ring of 3-8 shared-memory buffers (as many steps of ~1024 pixels as fit into
+// 72 KB): it issues the copies of step s+nst-1 (ASYNC: 16-byte asynchronous copies, two flow pixels / sixteen mask
+// bytes each, starting at the aligned address below the first pixel), then folds step s while up to seven later
+// steps are in flight — with under three resident warps per SM that depth is what keeps HBM busy.  (Measured alternatives: a 4-warp CTA with
 // one folding warp spends its time in __syncthreads hand-offs — 41 us at 4K against 16 us here.)
 // Lane t folds the pixels of cell t in raster order — rows top to bottom, columns left to right — which is the
 // order in which the reference's loop reaches that cell, so sums and counts are bit-identical:
@@ -419,15 +420,17 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
         const int cw = min(span, FC_CAP - 4);          // pixels per row of one step
         const int pitchf = (cw + 3) & ~1;              // row pitch of the flow buffer (pixels; even, >= cw + 2)
         const int pitchm = (cw + 30) & ~15;            // row pitch of the mask buffer (bytes; multiple of 16, >= cw + 15)
-        const int rg = max(1, min(FC_CAP / pitchf, FC_MCAP / pitchm));   // rows per step; > 1 only when cw == span
+        const int rg = max(1, FC_STEP_PX / pitchf);    // rows per step; > 1 only when cw == span
+        const int fbytes = rg * pitchf * 8, sbytes = fbytes + rg * pitchm;   // one staging buffer: flow rows, then mask rows
+        const int nst = min(FC_MAX_NST, FC_SMEM_BYTES / sbytes);             // ring depth: nst - 1 steps in flight
         const int ncs = (span + cw - 1) / cw, nrs = (rows + rg - 1) / rg, nsteps = ncs * nrs;
-        auto stage = [&](int s) {   // issue the copies of step s into buffer s % FC_NST, commit one group
+        auto stage = [&](int s) {   // issue the copies of step s into buffer s % nst, commit one group
             if (s < nsteps) {
                 const int ri = s / ncs, ci = s - ri * ncs;
                 const int r0 = y0 + ri * rg, nr = min(rg, y1 - r0);
                 const int cx0 = px0 + ci * cw, nc = min(cw, px1 - cx0);
-                float2* sf = reinterpret_cast<float2*>(dyn + (s % FC_NST) * FC_STAGE_BYTES);
-                uint8_t* sm = dyn + (s % FC_NST) * FC_STAGE_BYTES + FC_CAP * 8;
+                float2* sf = reinterpret_cast<float2*>(dyn + (s % nst) * sbytes);
+                uint8_t* sm = dyn + (s % nst) * sbytes + fbytes;
                 if (ASYNC) {
                     const int ax0 = cx0 & ~1, nf = (cx0 + nc - ax0 + 1) >> 1;
                     for (int r = 0; r < nr; r++) {
@@ -455,19 +458,25 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
             }
             async_copy_commit();   // one group per call (possibly empty) keeps wait_group's count uniform
         };
-#pragma unroll
-        for (int s = 0; s < FC_NST - 1; s++) stage(s);
+        for (int s = 0; s < nst - 1; s++) stage(s);
         for (int s = 0; s < nsteps; s++) {
-            stage(s + FC_NST - 1);                 // into the buffer folded in the previous iteration
-            async_copy_wait<FC_NST - 1>();         // this lane's copies of step s have landed
+            stage(s + nst - 1);                    // into the buffer folded in the previous iteration
+            switch (nst) {                         // this lane's copies of step s have landed (nst - 1 newer groups may be pending)
+                case 3: async_copy_wait<2>(); break;
+                case 4: async_copy_wait<3>(); break;
+                case 5: async_copy_wait<4>(); break;
+                case 6: async_copy_wait<5>(); break;
+                case 7: async_copy_wait<6>(); break;
+                default: async_copy_wait<7>(); break;
+            }
             __syncwarp();                          // ... and the other lanes' too
             if (owner) {
                 const int ri = s / ncs, ci = s - ri * ncs;
                 const int r0 = y0 + ri * rg, nr = min(rg, y1 - r0);
                 const int cx0 = px0 + ci * cw, nc = min(cw, px1 - cx0);
                 const int a = max(xa, cx0) - cx0, b = min(xb, cx0 + nc) - cx0;
-                const float2* sf = reinterpret_cast<const float2*>(dyn + (s % FC_NST) * FC_STAGE_BYTES) + (ASYNC ? (cx0 & 1) : 0);
-                const uint8_t* sm = dyn + (s % FC_NST) * FC_STAGE_BYTES + FC_CAP * 8 + (ASYNC ? (cx0 & 15) : 0);
+                const float2* sf = reinterpret_cast<const float2*>(dyn + (s % nst) * sbytes) + (ASYNC ? (cx0 & 1) : 0);
+                const uint8_t* sm = dyn + (s % nst) * sbytes + fbytes + (ASYNC ? (cx0 & 15) : 0);
                 for (int r = 0; r < nr; r++) {
                     const float2* fr = sf + r * pitchf;
                     const uint8_t* mr = sm + r * pitchm;
@@ -494,7 +503,7 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
                     }
                 }
             }
-            __syncwarp();   // buffer s % FC_NST is free for the copies of step s + FC_NST
+            __syncwarp();   // buffer s % nst is free for the copies of step s + nst
         }
     }
     if (owner) {
@@ -540,39 +549,44 @@ __global__ void __launch_bounds__(1024) flow_emit_cells_kernel(const CellRec* __
 {
     __shared__ uint32_t warp_tot[32];
     const float gx = __fdiv_rn(1.0f, (float)gw), gy = __fdiv_rn(1.0f, (float)gh);
-    const long long total = (long long)gw * gh;
+    const int total = gw * gh;   // <= 2^30 (host-checked)
+    const uint4* recs = reinterpret_cast<const uint4*>(cells);
     unsigned long long base = 0;
-    for (long long k0 = 0; k0 < total; k0 += (long long)blockDim.x * FE_PER) {
-        const long long kb = k0 + (long long)threadIdx.x * FE_PER;
+    for (int k0 = 0; k0 < total; k0 += (int)blockDim.x * FE_PER) {
+        const int kb = k0 + (int)threadIdx.x * FE_PER;
+        const int xs0 = kb < total ? kb / gh : 0, ys0 = kb < total ? kb - xs0 * gh : 0;
         uint32_t flags = 0;
         uint4 rec[FE_PER];   // the records stay in registers: the ordered writes below need no second load
+        {
+            int x = xs0, y = ys0;
 #pragma unroll
-        for (int j = 0; j < FE_PER; j++) {
-            const long long k = kb + j;
-            rec[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (k < total) {
-                const int x = (int)(k / gh), y = (int)(k - (long long)x * gh);
-                rec[j] = __ldg(reinterpret_cast<const uint4*>(cells) + ((size_t)y * gw + x));
+            for (int j = 0; j < FE_PER; j++) {
+                rec[j] = make_uint4(0u, 0u, 0u, 0u);
+                if (kb + j < total) rec[j] = __ldg(recs + ((size_t)y * gw + x));
+                flags |= (rec[j].z & 1u) << j;
+                if (++y == gh) { y = 0; x++; }
             }
-            flags |= (rec[j].z & 1u) << j;
         }
         uint32_t tot;
         unsigned long long pos = base + block_excl_scan(__popc(flags), warp_tot, &tot);
+        {
+            int x = xs0, y = ys0;
 #pragma unroll
-        for (int j = 0; j < FE_PER; j++)
-            if ((flags >> j) & 1u) {
-                const long long k = kb + j;
-                const int x = (int)(k / gh), y = (int)(k - (long long)x * gh);
-                if (pos < cap) {
-                    ofps_mv e;
-                    e.px = __fmul_rn(__fadd_rn((float)x, 0.5f), gx);
-                    e.py = __fmul_rn(__fadd_rn((float)y, 0.5f), gy);
-                    e.mx = __uint_as_float(rec[j].x);
-                    e.my = __uint_as_float(rec[j].y);
-                    out[pos] = e;
+            for (int j = 0; j < FE_PER; j++) {
+                if ((flags >> j) & 1u) {
+                    if (pos < cap) {
+                        ofps_mv e;
+                        e.px = __fmul_rn(__fadd_rn((float)x, 0.5f), gx);
+                        e.py = __fmul_rn(__fadd_rn((float)y, 0.5f), gy);
+                        e.mx = __uint_as_float(rec[j].x);
+                        e.my = __uint_as_float(rec[j].y);
+                        out[pos] = e;
+                    }
+                    pos++;
                 }
-                pos++;
+                if (++y == gh) { y = 0; x++; }
             }
+        }
         base += tot;
     }
     if (threadIdx.x == 0) *n_out = base;
