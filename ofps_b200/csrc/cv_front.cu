@@ -44,6 +44,19 @@ __device__ __forceinline__ void async_copy16(void* smem, const void* gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 #endif
 }
+// shared-memory destination as a plain byte address: computed once per step, advanced by adds in the copy loops
+#ifdef OFPSB_EMU
+typedef uint8_t* smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(void* p) { return static_cast<uint8_t*>(p); }
+__device__ __forceinline__ void async_copy16_to(smem_addr_t dst, const void* gmem) { memcpy(dst, gmem, 16); }
+#else
+typedef uint32_t smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void async_copy16_to(smem_addr_t dst, const void* gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem) : "memory");
+}
+#endif
 __device__ __forceinline__ void async_copy_commit()
 {
 #ifndef OFPSB_EMU
@@ -383,7 +396,7 @@ __device__ __forceinline__ int cell_start(int c, int len, float inv, float gm1)
 constexpr float F32_EPSILON = 1.1920928955078125e-07f;
 constexpr int FC_NC = 32;         // cells per CTA = one warp: adjacent cells of one cell row, one lane each
 constexpr int FC_CAP = 2048;      // most pixels of one row in a step (wider spans are walked in chunks)
-constexpr int FC_STEP_PX = 1024;  // rows are grouped into steps of about this many pixels
+constexpr int FC_STEP_PX = 2048;  // rows are grouped into steps of about this many pixels
 constexpr int FC_MAX_NST = 8;     // most staging buffers in the ring
 constexpr int FC_SMEM_BYTES = 72 * 1024;   // dynamic shared memory per CTA (3 CTAs per SM): the ring takes as many
                                            // buffers of the step's size as fit, at least 3 (FC_CAP * 8 + mask < 24 KB)
@@ -424,28 +437,36 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
         const int fbytes = rg * pitchf * 8, sbytes = fbytes + rg * pitchm;   // one staging buffer: flow rows, then mask rows
         const int nst = min(FC_MAX_NST, FC_SMEM_BYTES / sbytes);             // ring depth: nst - 1 steps in flight
         const int ncs = (span + cw - 1) / cw, nrs = (rows + rg - 1) / rg, nsteps = ncs * nrs;
-        auto stage = [&](int s) {   // issue the copies of step s into buffer s % nst, commit one group
-            if (s < nsteps) {
-                const int ri = s / ncs, ci = s - ri * ncs;
-                const int r0 = y0 + ri * rg, nr = min(rg, y1 - r0);
-                const int cx0 = px0 + ci * cw, nc = min(cw, px1 - cx0);
-                float2* sf = reinterpret_cast<float2*>(dyn + (s % nst) * sbytes);
-                uint8_t* sm = dyn + (s % nst) * sbytes + fbytes;
+        // step s = (row group ri, column chunk ci), buffer s % nst — kept incrementally for the staging side (p_*) and
+        // the folding side (c_*): no divisions on the warp's critical path
+        int p_s = 0, p_ri = 0, p_ci = 0, p_buf = 0;
+        auto stage = [&]() {   // issue the copies of the next step into its buffer, commit one group
+            if (p_s < nsteps) {
+                const int r0 = y0 + p_ri * rg, nr = min(rg, y1 - r0);
+                const int cx0 = px0 + p_ci * cw, nc = min(cw, px1 - cx0);
+                uint8_t* buf = dyn + p_buf * sbytes;
                 if (ASYNC) {
                     const int ax0 = cx0 & ~1, nf = (cx0 + nc - ax0 + 1) >> 1;
-                    for (int r = 0; r < nr; r++) {
-                        const float* frow = flow + (long long)(r0 + r) * flow_stride + 2ll * ax0;
-                        float2* srow = sf + r * pitchf;
-                        for (int k = lane; k < nf; k += 32) async_copy16(srow + 2 * k, frow + 4 * k);
+                    const char* g = reinterpret_cast<const char*>(flow + (long long)r0 * flow_stride + 2ll * ax0) + 16 * lane;
+                    smem_addr_t d = smem_addr(buf) + 16 * lane;
+                    for (int r = 0; r < nr; r++, g += flow_stride * 4, d += pitchf * 8) {
+                        const char* gk = g;
+                        smem_addr_t dk = d;
+                        for (int k = lane; k < nf; k += 32, gk += 512, dk += 512) async_copy16_to(dk, gk);
                     }
                     if (mask) {
                         const int am0 = cx0 & ~15, nm = (cx0 + nc - am0 + 15) >> 4;
-                        for (int r = 0; r < nr; r++) {
-                            const uint8_t* mrow = mask + (long long)(r0 + r) * mask_stride + am0;
-                            for (int k = lane; k < nm; k += 32) async_copy16(sm + r * pitchm + 16 * k, mrow + 16 * k);
+                        const uint8_t* m = mask + (long long)r0 * mask_stride + am0 + 16 * lane;
+                        smem_addr_t dm = smem_addr(buf + fbytes) + 16 * lane;
+                        for (int r = 0; r < nr; r++, m += mask_stride, dm += pitchm) {
+                            const uint8_t* mk = m;
+                            smem_addr_t dk = dm;
+                            for (int k = lane; k < nm; k += 32, mk += 512, dk += 512) async_copy16_to(dk, mk);
                         }
                     }
                 } else {
+                    float2* sf = reinterpret_cast<float2*>(buf);
+                    uint8_t* sm = buf + fbytes;
                     for (int r = 0; r < nr; r++) {
                         const float* frow = flow + (long long)(r0 + r) * flow_stride + 2ll * cx0;
                         for (int c = lane; c < nc; c += 32) sf[r * pitchf + c] = make_float2(__ldg(frow + 2 * c), __ldg(frow + 2 * c + 1));
@@ -455,12 +476,16 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
                         }
                     }
                 }
+                p_s++;
+                if (++p_ci == ncs) { p_ci = 0; p_ri++; }
+                if (++p_buf == nst) p_buf = 0;
             }
             async_copy_commit();   // one group per call (possibly empty) keeps wait_group's count uniform
         };
-        for (int s = 0; s < nst - 1; s++) stage(s);
+        for (int s = 0; s < nst - 1; s++) stage();
+        int c_ri = 0, c_ci = 0, c_buf = 0;
         for (int s = 0; s < nsteps; s++) {
-            stage(s + nst - 1);                    // into the buffer folded in the previous iteration
+            stage();                               // step s + nst - 1, into the buffer folded in the previous iteration
             switch (nst) {                         // this lane's copies of step s have landed (nst - 1 newer groups may be pending)
                 case 3: async_copy_wait<2>(); break;
                 case 4: async_copy_wait<3>(); break;
@@ -471,12 +496,11 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
             }
             __syncwarp();                          // ... and the other lanes' too
             if (owner) {
-                const int ri = s / ncs, ci = s - ri * ncs;
-                const int r0 = y0 + ri * rg, nr = min(rg, y1 - r0);
-                const int cx0 = px0 + ci * cw, nc = min(cw, px1 - cx0);
+                const int r0 = y0 + c_ri * rg, nr = min(rg, y1 - r0);
+                const int cx0 = px0 + c_ci * cw, nc = min(cw, px1 - cx0);
                 const int a = max(xa, cx0) - cx0, b = min(xb, cx0 + nc) - cx0;
-                const float2* sf = reinterpret_cast<const float2*>(dyn + (s % nst) * sbytes) + (ASYNC ? (cx0 & 1) : 0);
-                const uint8_t* sm = dyn + (s % nst) * sbytes + fbytes + (ASYNC ? (cx0 & 15) : 0);
+                const float2* sf = reinterpret_cast<const float2*>(dyn + c_buf * sbytes) + (ASYNC ? (cx0 & 1) : 0);
+                const uint8_t* sm = dyn + c_buf * sbytes + fbytes + (ASYNC ? (cx0 & 15) : 0);
                 for (int r = 0; r < nr; r++) {
                     const float2* fr = sf + r * pitchf;
                     const uint8_t* mr = sm + r * pitchm;
@@ -503,6 +527,8 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
                     }
                 }
             }
+            if (++c_ci == ncs) { c_ci = 0; c_ri++; }
+            if (++c_buf == nst) c_buf = 0;
             __syncwarp();   // buffer s % nst is free for the copies of step s + nst
         }
     }
@@ -512,7 +538,7 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
         rec.my = __fdiv_rn(sy, cnt);
         rec.touched = cnt > 0.5f ? 1u : 0u;   // counts start at f32::EPSILON and grow by 1.0 per vector
         rec.pad = 0u;
-        cells[(size_t)cy * gw + cell] = rec;
+        cells[(size_t)cell * gh + cy] = rec;   // column-major: the order flow_emit_cells_kernel walks
     }
 }
 
@@ -557,15 +583,11 @@ __global__ void __launch_bounds__(1024) flow_emit_cells_kernel(const CellRec* __
         const int xs0 = kb < total ? kb / gh : 0, ys0 = kb < total ? kb - xs0 * gh : 0;
         uint32_t flags = 0;
         uint4 rec[FE_PER];   // the records stay in registers: the ordered writes below need no second load
-        {
-            int x = xs0, y = ys0;
 #pragma unroll
-            for (int j = 0; j < FE_PER; j++) {
-                rec[j] = make_uint4(0u, 0u, 0u, 0u);
-                if (kb + j < total) rec[j] = __ldg(recs + ((size_t)y * gw + x));
-                flags |= (rec[j].z & 1u) << j;
-                if (++y == gh) { y = 0; x++; }
-            }
+        for (int j = 0; j < FE_PER; j++) {
+            rec[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (kb + j < total) rec[j] = __ldg(recs + kb + j);   // records are stored in this (x, y) order
+            flags |= (rec[j].z & 1u) << j;
         }
         uint32_t tot;
         unsigned long long pos = base + block_excl_scan(__popc(flags), warp_tot, &tot);
