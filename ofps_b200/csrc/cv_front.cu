@@ -415,7 +415,8 @@ struct __align__(16) CellRec { float mx, my; uint32_t touched, pad; };
 template <bool ASYNC>
 __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict__ flow, long long flow_stride,
                                                         const uint8_t* __restrict__ mask, long long mask_stride,
-                                                        int w, int h, int gw, int gh, CellRec* __restrict__ cells)
+                                                        int w, int h, int gw, int gh, CellRec* __restrict__ cells,
+                                                        uint32_t* __restrict__ colcount)
 {
     OFPSB_DYN_SMEM(dyn);
     const int lane = threadIdx.x;
@@ -539,6 +540,7 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
         rec.touched = cnt > 0.5f ? 1u : 0u;   // counts start at f32::EPSILON and grow by 1.0 per vector
         rec.pad = 0u;
         cells[(size_t)cell * gh + cy] = rec;   // column-major: the order flow_emit_cells_kernel walks
+        if (rec.touched) atomicAdd(&colcount[cell], 1u);   // touched cells per column (integer: order-free)
     }
 }
 
@@ -566,52 +568,71 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_t
 }
 
 // Touched cells in (x, y) lexicographic order (BTreeSet<(usize, usize)>, cv-decoder:243, 276) -> entries:
-// pos = (x + 0.5, y + 0.5) .* (1/gw, 1/gh), motion = cell mean.  One CTA; every thread owns FE_PER consecutive
-// positions of the column-major order per pass: independent flag loads, one block scan per pass, ordered writes.
-constexpr int FE_PER = 8;
-__global__ void __launch_bounds__(1024) flow_emit_cells_kernel(const CellRec* __restrict__ cells, int gw, int gh,
-                                                               ofps_mv* __restrict__ out, unsigned long long cap,
-                                                               unsigned long long* __restrict__ n_out)
+// pos = (x + 0.5, y + 0.5) .* (1/gw, 1/gh), motion = cell mean.  One warp per cell column: the entries of column x
+// start at the number of touched cells in the columns before it (colcount, summed per CTA), and inside the column a
+// ballot ranks the touched cells, so a warp writes its entries to consecutive addresses.
+constexpr int FE_WARPS = 8;
+__global__ void __launch_bounds__(32 * FE_WARPS) flow_emit_cells_kernel(const CellRec* __restrict__ cells,
+                                                                        const uint32_t* __restrict__ colcount, int gw, int gh,
+                                                                        ofps_mv* __restrict__ out, unsigned long long cap,
+                                                                        unsigned long long* __restrict__ n_out)
 {
-    __shared__ uint32_t warp_tot[32];
-    const float gx = __fdiv_rn(1.0f, (float)gw), gy = __fdiv_rn(1.0f, (float)gh);
-    const int total = gw * gh;   // <= 2^30 (host-checked)
-    const uint4* recs = reinterpret_cast<const uint4*>(cells);
-    unsigned long long base = 0;
-    for (int k0 = 0; k0 < total; k0 += (int)blockDim.x * FE_PER) {
-        const int kb = k0 + (int)threadIdx.x * FE_PER;
-        const int xs0 = kb < total ? kb / gh : 0, ys0 = kb < total ? kb - xs0 * gh : 0;
-        uint32_t flags = 0;
-        uint4 rec[FE_PER];   // the records stay in registers: the ordered writes below need no second load
-#pragma unroll
-        for (int j = 0; j < FE_PER; j++) {
-            rec[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (kb + j < total) rec[j] = __ldg(recs + kb + j);   // records are stored in this (x, y) order
-            flags |= (rec[j].z & 1u) << j;
+    __shared__ unsigned long long s_part[FE_WARPS];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int xfirst = blockIdx.x * FE_WARPS;
+    // touched cells in the columns before this CTA's first one (the last CTA also totals everything for *n_out)
+    const int upto = blockIdx.x == gridDim.x - 1 ? gw : xfirst;
+    unsigned long long before = 0, all = 0;
+    for (int i = threadIdx.x; i < upto; i += blockDim.x) {
+        const uint32_t c = __ldg(colcount + i);
+        all += c;
+        if (i < xfirst) before += c;
+    }
+    for (int pass = 0; pass < 2; pass++) {   // block sum of `before`, then of `all`
+        unsigned long long v = pass == 0 ? before : all;
+        uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+        for (int d = 16; d > 0; d >>= 1) {
+            const uint32_t lo2 = __shfl_xor_sync(0xffffffffu, lo, d), hi2 = __shfl_xor_sync(0xffffffffu, hi, d);
+            v = (((unsigned long long)hi << 32) | lo) + (((unsigned long long)hi2 << 32) | lo2);
+            lo = (uint32_t)v;
+            hi = (uint32_t)(v >> 32);
         }
-        uint32_t tot;
-        unsigned long long pos = base + block_excl_scan(__popc(flags), warp_tot, &tot);
-        {
-            int x = xs0, y = ys0;
-#pragma unroll
-            for (int j = 0; j < FE_PER; j++) {
-                if ((flags >> j) & 1u) {
-                    if (pos < cap) {
-                        ofps_mv e;
-                        e.px = __fmul_rn(__fadd_rn((float)x, 0.5f), gx);
-                        e.py = __fmul_rn(__fadd_rn((float)y, 0.5f), gy);
-                        e.mx = __uint_as_float(rec[j].x);
-                        e.my = __uint_as_float(rec[j].y);
-                        out[pos] = e;
-                    }
-                    pos++;
-                }
-                if (++y == gh) { y = 0; x++; }
+        __syncthreads();   // s_part is reused by the second pass
+        if (lane == 0) s_part[wid] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t = 0;
+            for (int k = 0; k < FE_WARPS; k++) t += s_part[k];
+            if (pass == 0) s_base = t;
+            else if (blockIdx.x == gridDim.x - 1) *n_out = t;
+        }
+    }
+    __syncthreads();
+    const int x = xfirst + wid;
+    if (x >= gw) return;
+    unsigned long long pos = s_base;
+    for (int k = 0; k < wid; k++) pos += __ldg(colcount + xfirst + k);
+    const float gx = __fdiv_rn(1.0f, (float)gw), gy = __fdiv_rn(1.0f, (float)gh);
+    const uint4* col = reinterpret_cast<const uint4*>(cells) + (size_t)x * gh;   // records are column-major
+    for (int y0 = 0; y0 < gh; y0 += 32) {
+        const int y = y0 + lane;
+        uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+        if (y < gh) rec = __ldg(col + y);
+        const unsigned m = __ballot_sync(0xffffffffu, (rec.z & 1u) != 0);
+        if (rec.z & 1u) {
+            const unsigned long long p = pos + __popc(m & ((1u << lane) - 1u));
+            if (p < cap) {
+                float4 e;
+                e.x = __fmul_rn(__fadd_rn((float)x, 0.5f), gx);
+                e.y = __fmul_rn(__fadd_rn((float)y, 0.5f), gy);
+                e.z = __uint_as_float(rec.x);
+                e.w = __uint_as_float(rec.y);
+                *reinterpret_cast<float4*>(out + p) = e;
             }
         }
-        base += tot;
+        pos += __popc(m);
     }
-    if (threadIdx.x == 0) *n_out = base;
 }
 
 // Per-pixel variant (process_fullres = false): every kept pixel becomes an entry, raster order.
@@ -788,6 +809,10 @@ int launch_flow_entries(const float* d_flow, size_t flow_stride, const uint8_t* 
         set_error("flow_entries: %dx%d frame: pixel-centre positions reach 0 or 1 in f32", w, h);
         return OFPSB_E_INVALID;
     }
+    if (reinterpret_cast<uintptr_t>(d_entries) & 15u) {
+        set_error("flow_entries: the entry buffer must be 16-byte aligned");
+        return OFPSB_E_INVALID;
+    }
     const long long npix = (long long)w * h;
     if (gw == 0) {   // per pixel
         const long long ntiles = (npix + FP_TILE - 1) / FP_TILE;
@@ -813,7 +838,10 @@ int launch_flow_entries(const float* d_flow, size_t flow_stride, const uint8_t* 
     }
     const int igw = (int)gw, igh = (int)gh;
     if (int rc = scratch.cells.reserve(gw * gh * sizeof(CellRec))) return rc;
+    if (int rc = scratch.bounds.reserve(gw * sizeof(uint32_t))) return rc;
     CellRec* cells = scratch.cells.as<CellRec>();
+    uint32_t* colcount = scratch.bounds.as<uint32_t>();
+    OFPSB_CUDA_TRY(cudaMemsetAsync(colcount, 0, gw * sizeof(uint32_t), stream));
     const dim3 grid((unsigned)((igw + FC_NC - 1) / FC_NC), (unsigned)igh);
     // 16-byte asynchronous staging needs 16-byte aligned flow rows (and mask rows, when there is a mask)
     const bool async = ((reinterpret_cast<uintptr_t>(d_flow) & 15u) | (flow_stride & 3u)) == 0 &&
@@ -831,11 +859,12 @@ int launch_flow_entries(const float* d_flow, size_t flow_stride, const uint8_t* 
 #endif
     if (async)
         OFPSB_LAUNCH_SMEM(flow_cells_kernel<true>, grid, 32, FC_SMEM_BYTES, stream, d_flow, (long long)flow_stride, d_mask,
-                          (long long)mask_stride, w, h, igw, igh, cells);
+                          (long long)mask_stride, w, h, igw, igh, cells, colcount);
     else
         OFPSB_LAUNCH_SMEM(flow_cells_kernel<false>, grid, 32, FC_SMEM_BYTES, stream, d_flow, (long long)flow_stride, d_mask,
-                          (long long)mask_stride, w, h, igw, igh, cells);
-    OFPSB_LAUNCH(flow_emit_cells_kernel, 1, 1024, stream, cells, igw, igh, d_entries, cap, d_count);
+                          (long long)mask_stride, w, h, igw, igh, cells, colcount);
+    OFPSB_LAUNCH(flow_emit_cells_kernel, (unsigned)((igw + FE_WARPS - 1) / FE_WARPS), 32 * FE_WARPS, stream, cells, colcount, igw, igh,
+                 d_entries, cap, d_count);
     OFPSB_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += 2;
     return OFPSB_OK;
