@@ -13,6 +13,8 @@
 // sums of K9 follow the reference's raster order with un-fused arithmetic (--fmad=false, explicit _rn ops).
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace ofpsb {
 
 namespace {
@@ -398,6 +400,8 @@ constexpr int FC_NC = 32;         // cells per CTA = one warp: adjacent cells of
 constexpr int FC_CAP = 2048;      // most pixels of one row in a step (wider spans are walked in chunks)
 constexpr int FC_STEP_PX = 2048;  // rows are grouped into steps of about this many pixels
 constexpr int FC_MAX_NST = 8;     // most staging buffers in the ring
+constexpr int FC_UNR = 8;         // pixels per fold group
+constexpr int FC_SMEM_PAD = 128;  // the fold may load up to FC_UNR - 1 pixels past the end of the last buffer
 constexpr int FC_SMEM_BYTES = 72 * 1024;   // dynamic shared memory per CTA (3 CTAs per SM): the ring takes as many
                                            // buffers of the step's size as fit, at least 3 (FC_CAP * 8 + mask < 24 KB)
 
@@ -505,27 +509,31 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
                 for (int r = 0; r < nr; r++) {
                     const float2* fr = sf + r * pitchf;
                     const uint8_t* mr = sm + r * pitchm;
-                    if (mask) {
-#pragma unroll 4
-                        for (int c = a; c < b; c++) {
-                            float2 f = fr[c];
-                            const bool keep = mr[c] != 0;   // `*mask < 0.1` -> skip (cv-decoder:258)
-                            OFPSB_KEEP_LOADED(f.x, f.y);    // the flow load must not wait for the mask byte
-                            if (keep) {
+                    // Groups of FC_UNR pixels: all loads of a group are issued before the first add, so the warp waits
+                    // for shared memory once per group; slots past the cell's last pixel are loaded (the buffers are
+                    // padded) but predicated off, which also removes any remainder loop.
+                    auto group = [&](int c, auto tail) {   // tail: the last, partial group of the row checks c + j < b
+                        constexpr bool TAIL = decltype(tail)::value;
+                        float2 f[FC_UNR];
+                        uint32_t m[FC_UNR];
+#pragma unroll
+                        for (int j = 0; j < FC_UNR; j++) {
+                            f[j] = fr[c + j];
+                            m[j] = mask ? (uint32_t)mr[c + j] : 1u;   // `*mask < 0.1` -> skip (cv-decoder:258)
+                        }
+#pragma unroll
+                        for (int j = 0; j < FC_UNR; j++) OFPSB_KEEP_LOADED(f[j].x, f[j].y);
+#pragma unroll
+                        for (int j = 0; j < FC_UNR; j++)
+                            if ((!TAIL || c + j < b) && m[j] != 0u) {
                                 cnt = __fadd_rn(cnt, 1.0f);
-                                sx = __fadd_rn(__fmul_rn(f.x, nx), sx);
-                                sy = __fadd_rn(__fmul_rn(f.y, ny), sy);
+                                sx = __fadd_rn(__fmul_rn(f[j].x, nx), sx);
+                                sy = __fadd_rn(__fmul_rn(f[j].y, ny), sy);
                             }
-                        }
-                    } else {
-#pragma unroll 4
-                        for (int c = a; c < b; c++) {
-                            const float2 f = fr[c];
-                            cnt = __fadd_rn(cnt, 1.0f);
-                            sx = __fadd_rn(__fmul_rn(f.x, nx), sx);
-                            sy = __fadd_rn(__fmul_rn(f.y, ny), sy);
-                        }
-                    }
+                    };
+                    int c = a;
+                    for (; c + FC_UNR <= b; c += FC_UNR) group(c, std::false_type{});
+                    if (c < b) group(c, std::true_type{});
                 }
             }
             if (++c_ci == ncs) { c_ci = 0; c_ri++; }
@@ -852,16 +860,16 @@ int launch_flow_entries(const float* d_flow, size_t flow_stride, const uint8_t* 
     OFPSB_CUDA_TRY(cudaGetDevice(&dev));
     bool& smem_opt_in = smem_opt_in_dev[dev & 63];
     if (!smem_opt_in) {
-        OFPSB_CUDA_TRY(cudaFuncSetAttribute(flow_cells_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
-        OFPSB_CUDA_TRY(cudaFuncSetAttribute(flow_cells_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
+        OFPSB_CUDA_TRY(cudaFuncSetAttribute(flow_cells_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES + FC_SMEM_PAD));
+        OFPSB_CUDA_TRY(cudaFuncSetAttribute(flow_cells_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES + FC_SMEM_PAD));
         smem_opt_in = true;
     }
 #endif
     if (async)
-        OFPSB_LAUNCH_SMEM(flow_cells_kernel<true>, grid, 32, FC_SMEM_BYTES, stream, d_flow, (long long)flow_stride, d_mask,
+        OFPSB_LAUNCH_SMEM(flow_cells_kernel<true>, grid, 32, FC_SMEM_BYTES + FC_SMEM_PAD, stream, d_flow, (long long)flow_stride, d_mask,
                           (long long)mask_stride, w, h, igw, igh, cells, colcount);
     else
-        OFPSB_LAUNCH_SMEM(flow_cells_kernel<false>, grid, 32, FC_SMEM_BYTES, stream, d_flow, (long long)flow_stride, d_mask,
+        OFPSB_LAUNCH_SMEM(flow_cells_kernel<false>, grid, 32, FC_SMEM_BYTES + FC_SMEM_PAD, stream, d_flow, (long long)flow_stride, d_mask,
                           (long long)mask_stride, w, h, igw, igh, cells, colcount);
     OFPSB_LAUNCH(flow_emit_cells_kernel, (unsigned)((igw + FE_WARPS - 1) / FE_WARPS), 32 * FE_WARPS, stream, cells, colcount, igw, igh,
                  d_entries, cap, d_count);
