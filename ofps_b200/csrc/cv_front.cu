@@ -248,22 +248,29 @@ __global__ void __launch_bounds__(CM_NT) contrast_mask_kernel(const uint8_t* __r
     const int t0 = blockIdx.x * CM_TW, ty0 = blockIdx.y * CM_TH;
     const int gx0 = t0 - 16, gy0 = ty0 - 7;
 
-    // (1) gray tile
+    // (1) gray tile: whole 16-byte chunks inside the frame by asynchronous copies (a reflected ROW only changes the
+    //     source row); the bytes of chunks that cross the left / right frame border are gathered one per thread
     {
         constexpr int CPR = CM_GW / 16;   // chunks per row
         const bool aligned = ((reinterpret_cast<uintptr_t>(gray) | (uintptr_t)stride) & 15u) == 0;
+        const bool rows_inside = gy0 >= 0 && gy0 + CM_GH <= h;
+        // chunk k is copied whole iff it lies inside the frame: k in [k_lo, k_hi)
+        const int k_lo = aligned ? max(0, (-gx0 + 15) >> 4) : CPR;
+        const int k_hi = aligned ? min(CPR, (w - gx0) >> 4) : 0;
         for (int i = tid; i < CM_GH * CPR; i += CM_NT) {
             const int r = i / CPR, k = i - r * CPR;
-            const int x = gx0 + 16 * k;
-            const uint8_t* row = gray + (size_t)reflect101(gy0 + r, h) * stride;
-            if (aligned && x >= 0 && x + 16 <= w) {
-                async_copy16(&G[r][16 * k], row + x);
-            } else {
-#pragma unroll 4
-                for (int j = 0; j < 16; j++) G[r][16 * k + j] = __ldg(row + reflect101(x + j, w));
+            if (k >= k_lo && k < k_hi) {
+                const int gy = rows_inside ? gy0 + r : reflect101(gy0 + r, h);
+                async_copy16(&G[r][16 * k], gray + (size_t)gy * stride + gx0 + 16 * k);
             }
         }
         async_copy_commit();
+        const int nb = (k_hi > k_lo ? CPR - (k_hi - k_lo) : CPR) * 16;   // gathered bytes per row
+        for (int i = tid; i < CM_GH * nb; i += CM_NT) {
+            const int r = i / nb, j = i - r * nb;
+            const int c = (k_hi > k_lo && j >= 16 * k_lo) ? j + 16 * (k_hi - k_lo) : j;   // skip the copied chunks
+            G[r][c] = __ldg(gray + (size_t)reflect101(gy0 + r, h) * stride + reflect101(gx0 + c, w));
+        }
         async_copy_wait<0>();
     }
     __syncthreads();
@@ -340,9 +347,10 @@ __global__ void __launch_bounds__(CM_NT) contrast_mask_kernel(const uint8_t* __r
         const int y = ty0 + orow, x0 = t0 + 32 * ow;
         if (y < h && x0 < w) {
             // 64-bit window of the threshold row of frame row y+dy (reflected into the frame): bit i <-> column x0-8+i
+            const bool rows_inside = ty0 - 5 >= 0 && ty0 + CM_TH + 5 <= h;   // tile-uniform: no row of the window is reflected
             auto win = [&](int dy) -> unsigned long long {
                 int py = y + dy;
-                if (py < 0 || py >= h) py = reflect101(py, h);
+                if (!rows_inside && (py < 0 || py >= h)) py = reflect101(py, h);
                 const uint32_t* t = T[py - (ty0 - 5)];
                 return (unsigned long long)t[ow] | ((unsigned long long)t[ow + 1] << 32);
             };
