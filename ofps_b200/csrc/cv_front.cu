@@ -265,11 +265,17 @@ __global__ void __launch_bounds__(CM_NT) contrast_mask_kernel(const uint8_t* __r
             }
         }
         async_copy_commit();
-        const int nb = (k_hi > k_lo ? CPR - (k_hi - k_lo) : CPR) * 16;   // gathered bytes per row
-        for (int i = tid; i < CM_GH * nb; i += CM_NT) {
-            const int r = i / nb, j = i - r * nb;
-            const int c = (k_hi > k_lo && j >= 16 * k_lo) ? j + 16 * (k_hi - k_lo) : j;   // skip the copied chunks
-            G[r][c] = __ldg(gray + (size_t)reflect101(gy0 + r, h) * stride + reflect101(gx0 + c, w));
+        // Bytes the copies left out: in-frame pixels of partially covered chunks, and the two reflected columns on
+        // either side of the frame that the 5-tap row filter of an in-frame pixel reads.  (Threshold bits of
+        // out-of-frame columns are copied in step 3, never computed, so nothing further out is needed.)
+        const int c_lo = max(0, -2 - gx0), c_hi = min(CM_GW, w + 2 - gx0);
+        const int a_hi = k_hi > k_lo ? min(16 * k_lo, c_hi) : c_hi;        // segment A: [c_lo, a_hi)
+        const int b_lo = k_hi > k_lo ? max(16 * k_hi, c_lo) : c_hi;        // segment B: [b_lo, c_hi)
+        const int lane = tid & 31;
+        for (int r = tid >> 5; r < CM_GH; r += CM_NT / 32) {
+            const uint8_t* row = gray + (size_t)reflect101(gy0 + r, h) * stride;
+            for (int c = c_lo + lane; c < a_hi; c += 32) G[r][c] = __ldg(row + reflect101(gx0 + c, w));
+            for (int c = b_lo + lane; c < c_hi; c += 32) G[r][c] = __ldg(row + reflect101(gx0 + c, w));
         }
         async_copy_wait<0>();
     }
