@@ -18,6 +18,8 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
 #include <functional>
 #include <memory>
 #include <optional>
@@ -257,6 +259,84 @@ private:
     std::vector<uint8_t> prev_, cur_;
     MotionVectors scratch_;
     int have_ = 0;
+};
+
+// ---- Frame source for BlockMatchDecoder: 8-bit luma from a raw file or a YUV4MPEG2 (.y4m) stream.
+//   "WIDTHxHEIGHT@FPS:path"  raw luma planes back to back (the input string of the Rust `b200_block` shim,
+//                            rust/b200-block-decoder/src/lib.rs — the reference passes the decoder's input
+//                            string through unchanged, ofps/src/plugins/mod.rs:146-159)
+//   "path.y4m"               YUV4MPEG2: W / H / F from the header, Y plane of every FRAME (chroma skipped;
+//                            C420* / C422 / C444 / Cmono, 8 bit)
+class LumaFileSource {
+public:
+    explicit LumaFileSource(const std::string& input)
+    {
+        const auto colon = input.find(':');
+        const auto x = input.find('x');
+        // a geometry prefix is digits, 'x', '@' and '.' only, up to the first ':'
+        if (colon != std::string::npos && x != std::string::npos && x < colon &&
+            input.find_first_not_of("0123456789x@.", 0) == colon) {
+            const auto at = input.find('@');
+            w_ = std::atoi(input.substr(0, x).c_str());
+            h_ = std::atoi(input.substr(x + 1, (at != std::string::npos && at < colon ? at : colon) - x - 1).c_str());
+            if (at != std::string::npos && at < colon) fps_ = std::atof(input.substr(at + 1, colon - at - 1).c_str());
+            open(input.substr(colon + 1));
+            chroma_ = 0;
+        } else {
+            open(input);
+            char line[256];
+            if (!std::fgets(line, sizeof line, f_) || std::strncmp(line, "YUV4MPEG2", 9) != 0) fail("not a YUV4MPEG2 stream: " + input);
+            int cw = 2, ch = 2;   // chroma subsampling divisors; C420 is the format's default
+            for (char* tok = std::strtok(line + 9, " \n"); tok; tok = std::strtok(nullptr, " \n")) {
+                if (tok[0] == 'W') w_ = std::atoi(tok + 1);
+                else if (tok[0] == 'H') h_ = std::atoi(tok + 1);
+                else if (tok[0] == 'F') {
+                    int n = 0, d = 1;
+                    if (std::sscanf(tok + 1, "%d:%d", &n, &d) == 2 && d > 0) fps_ = (double)n / d;
+                } else if (tok[0] == 'C') {
+                    if (!std::strncmp(tok, "C420", 4)) { cw = 2; ch = 2; }
+                    else if (!std::strcmp(tok, "C422")) { cw = 2; ch = 1; }
+                    else if (!std::strcmp(tok, "C444")) { cw = 1; ch = 1; }
+                    else if (!std::strcmp(tok, "Cmono")) { cw = 0; ch = 0; }
+                    else fail(std::string("unsupported y4m colour space ") + tok);
+                }
+            }
+            if (w_ > 0 && h_ > 0) chroma_ = cw ? 2 * (size_t)((w_ + cw - 1) / cw) * (size_t)((h_ + ch - 1) / ch) : 0;
+            y4m_ = true;
+        }
+        if (w_ <= 0 || h_ <= 0) fail("bad frame size in " + input);
+    }
+    ~LumaFileSource() { if (f_) std::fclose(f_); }
+    LumaFileSource(const LumaFileSource&) = delete;
+    LumaFileSource& operator=(const LumaFileSource&) = delete;
+    int width() const { return w_; }
+    int height() const { return h_; }
+    double framerate() const { return fps_; }
+    // Fills width*height bytes; false at end of stream.  Usable directly as BlockMatchDecoder's frame source.
+    bool next(uint8_t* luma)
+    {
+        if (y4m_) {
+            char line[128];
+            if (!std::fgets(line, sizeof line, f_) || std::strncmp(line, "FRAME", 5) != 0) return false;
+        }
+        const size_t n = (size_t)w_ * h_;
+        if (std::fread(luma, 1, n, f_) != n) return false;
+        if (chroma_ && std::fseek(f_, (long)chroma_, SEEK_CUR) != 0) return false;
+        return true;
+    }
+
+private:
+    void open(const std::string& path)
+    {
+        f_ = std::fopen(path.c_str(), "rb");
+        if (!f_) fail("cannot open " + path);
+    }
+    [[noreturn]] void fail(const std::string& what) const { throw Error(OFPSB_E_IO, what); }
+    std::FILE* f_ = nullptr;
+    int w_ = 0, h_ = 0;
+    double fps_ = 0.0;
+    size_t chroma_ = 0;
+    bool y4m_ = false;
 };
 
 // ---- Decoder: the reference's cv-decoder (cv-decoder/src/lib.rs:17-307) with its two third-party calls
