@@ -421,28 +421,29 @@ constexpr int FC_SMEM_BYTES = 72 * 1024;   // dynamic shared memory per CTA (3 C
 
 struct __align__(16) CellRec { float mx, my; uint32_t touched, pad; };
 
-// One CTA = ONE WARP = FC_NC adjacent cells of one cell row; no block-wide barrier anywhere.  The warp streams the
-// pixel rows of its cells through a ring of 3-8 shared-memory buffers (as many steps of ~1024 pixels as fit into
-// 72 KB): it issues the copies of step s+nst-1 (ASYNC: 16-byte asynchronous copies, two flow pixels / sixteen mask
-// bytes each, starting at the aligned address below the first pixel), then folds step s while up to seven later
-// steps are in flight — with under three resident warps per SM that depth is what keeps HBM busy.  (Measured alternatives: a 4-warp CTA with
-// one folding warp spends its time in __syncthreads hand-offs — 41 us at 4K against 16 us here.)
+// One CTA = two warps = FC_NC adjacent cells of one cell row.  The pixel rows of those cells stream through a ring of
+// 3-8 shared-memory buffers (as many steps of ~2048 pixels as fit into 72 KB).  Warp 1 (the stager) issues the copies
+// of step s+nst-1 (ASYNC: 16-byte asynchronous copies, two flow pixels / sixteen mask bytes each, starting at the
+// aligned address below the first pixel) while warp 0 folds step s; one __syncthreads per step hands a landed buffer
+// over and takes the folded one back.  The fold is a single warp's dependent instruction stream (one instruction every
+// ~4 cycles, see profiles/r1_cv_front_ncu.md), so everything that is not an add of the reference's sum is kept off it.
 // Lane t folds the pixels of cell t in raster order — rows top to bottom, columns left to right — which is the
 // order in which the reference's loop reaches that cell, so sums and counts are bit-identical:
 //   counts += 1.0 (from f32::EPSILON), sum = motion * 1.0 + sum, motion = flow .* (1/W, 1/H).
 template <bool ASYNC>
-__global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict__ flow, long long flow_stride,
+__global__ void __launch_bounds__(64) flow_cells_kernel(const float* __restrict__ flow, long long flow_stride,
                                                         const uint8_t* __restrict__ mask, long long mask_stride,
                                                         int w, int h, int gw, int gh, CellRec* __restrict__ cells,
                                                         uint32_t* __restrict__ colcount)
 {
     OFPSB_DYN_SMEM(dyn);
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool stager = threadIdx.x >= 32;   // warp 1 keeps the copies in flight, warp 0 folds
     const int cy = blockIdx.y, c0 = blockIdx.x * FC_NC;
     const float nx = __fdiv_rn(1.0f, (float)w), ny = __fdiv_rn(1.0f, (float)h);
     const float gxm1 = (float)(gw - 1), gym1 = (float)(gh - 1);
     const int cell = c0 + lane;
-    const bool owner = cell < gw;
+    const bool owner = !stager && cell < gw;
     const int xa = cell_start(min(cell, gw), w, nx, gxm1), xb = cell_start(min(cell + 1, gw), w, nx, gxm1);
     const int px0 = __shfl_sync(0xffffffffu, xa, 0), px1 = __shfl_sync(0xffffffffu, xb, 31);
     const int y0 = cell_start(cy, h, ny, gym1), y1 = cell_start(cy + 1, h, ny, gym1);
@@ -501,19 +502,31 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
             }
             async_copy_commit();   // one group per call (possibly empty) keeps wait_group's count uniform
         };
-        for (int s = 0; s < nst - 1; s++) stage();
+        // Warp 1 runs nst - 1 steps ahead of warp 0; one __syncthreads per step hands a landed buffer over and takes
+        // the folded one back.  At the barrier that ends iteration s the copies of step s + 1 have landed
+        // (wait_group leaves the nst - 2 younger groups in flight) and step s has been folded, so its buffer —
+        // (s + nst) % nst — is the one the stager fills next.
+        auto wait_landed = [&]() {
+            switch (nst) {
+                case 3: async_copy_wait<1>(); break;
+                case 4: async_copy_wait<2>(); break;
+                case 5: async_copy_wait<3>(); break;
+                case 6: async_copy_wait<4>(); break;
+                case 7: async_copy_wait<5>(); break;
+                default: async_copy_wait<6>(); break;
+            }
+        };
+        if (stager) {
+            for (int s = 0; s < nst - 1; s++) stage();
+            wait_landed();   // step 0
+        }
+        __syncthreads();
         int c_ri = 0, c_ci = 0, c_buf = 0;
         for (int s = 0; s < nsteps; s++) {
-            stage();                               // step s + nst - 1, into the buffer folded in the previous iteration
-            switch (nst) {                         // this lane's copies of step s have landed (nst - 1 newer groups may be pending)
-                case 3: async_copy_wait<2>(); break;
-                case 4: async_copy_wait<3>(); break;
-                case 5: async_copy_wait<4>(); break;
-                case 6: async_copy_wait<5>(); break;
-                case 7: async_copy_wait<6>(); break;
-                default: async_copy_wait<7>(); break;
+            if (stager) {
+                stage();         // step s + nst - 1, into the buffer folded in the previous iteration
+                wait_landed();   // step s + 1
             }
-            __syncwarp();                          // ... and the other lanes' too
             if (owner) {
                 const int r0 = y0 + c_ri * rg, nr = min(rg, y1 - r0);
                 const int cx0 = px0 + c_ci * cw, nc = min(cw, px1 - cx0);
@@ -526,19 +539,20 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
                     // Groups of FC_UNR pixels: all loads of a group are issued before the first add, so the warp waits
                     // for shared memory once per group; slots past the cell's last pixel are loaded (the buffers are
                     // padded) but predicated off, which also removes any remainder loop.
-                    auto group = [&](int c, auto tail) {   // tail: the last, partial group of the row checks c + j < b
+                    auto group = [&](int c, auto tail, auto slots) {   // tail: the last, partial group of the row checks c + j < b
                         constexpr bool TAIL = decltype(tail)::value;
-                        float2 f[FC_UNR];
-                        uint32_t m[FC_UNR];
+                        constexpr int N = decltype(slots)::value;   // 8, or 4 for a short tail
+                        float2 f[N];
+                        uint32_t m[N];
 #pragma unroll
-                        for (int j = 0; j < FC_UNR; j++) {
+                        for (int j = 0; j < N; j++) {
                             f[j] = fr[c + j];
                             m[j] = mask ? (uint32_t)mr[c + j] : 1u;   // `*mask < 0.1` -> skip (cv-decoder:258)
                         }
 #pragma unroll
-                        for (int j = 0; j < FC_UNR; j++) OFPSB_KEEP_LOADED(f[j].x, f[j].y);
+                        for (int j = 0; j < N; j++) OFPSB_KEEP_LOADED(f[j].x, f[j].y);
 #pragma unroll
-                        for (int j = 0; j < FC_UNR; j++)
+                        for (int j = 0; j < N; j++)
                             if ((!TAIL || c + j < b) && m[j] != 0u) {
                                 cnt = __fadd_rn(cnt, 1.0f);
                                 sx = __fadd_rn(__fmul_rn(f[j].x, nx), sx);
@@ -546,13 +560,14 @@ __global__ void __launch_bounds__(32) flow_cells_kernel(const float* __restrict_
                             }
                     };
                     int c = a;
-                    for (; c + FC_UNR <= b; c += FC_UNR) group(c, std::false_type{});
-                    if (c < b) group(c, std::true_type{});
+                    for (; c + FC_UNR <= b; c += FC_UNR) group(c, std::false_type{}, std::integral_constant<int, FC_UNR>{});
+                    if (c + FC_UNR / 2 < b) group(c, std::true_type{}, std::integral_constant<int, FC_UNR>{});
+                    else if (c < b) group(c, std::true_type{}, std::integral_constant<int, FC_UNR / 2>{});
                 }
             }
             if (++c_ci == ncs) { c_ci = 0; c_ri++; }
             if (++c_buf == nst) c_buf = 0;
-            __syncwarp();   // buffer s % nst is free for the copies of step s + nst
+            __syncthreads();   // step s + 1 is visible to the folding warp, buffer s % nst is free for step s + nst
         }
     }
     if (owner) {
@@ -880,10 +895,10 @@ int launch_flow_entries(const float* d_flow, size_t flow_stride, const uint8_t* 
     }
 #endif
     if (async)
-        OFPSB_LAUNCH_SMEM(flow_cells_kernel<true>, grid, 32, FC_SMEM_BYTES + FC_SMEM_PAD, stream, d_flow, (long long)flow_stride, d_mask,
+        OFPSB_LAUNCH_SMEM(flow_cells_kernel<true>, grid, 64, FC_SMEM_BYTES + FC_SMEM_PAD, stream, d_flow, (long long)flow_stride, d_mask,
                           (long long)mask_stride, w, h, igw, igh, cells, colcount);
     else
-        OFPSB_LAUNCH_SMEM(flow_cells_kernel<false>, grid, 32, FC_SMEM_BYTES + FC_SMEM_PAD, stream, d_flow, (long long)flow_stride, d_mask,
+        OFPSB_LAUNCH_SMEM(flow_cells_kernel<false>, grid, 64, FC_SMEM_BYTES + FC_SMEM_PAD, stream, d_flow, (long long)flow_stride, d_mask,
                           (long long)mask_stride, w, h, igw, igh, cells, colcount);
     OFPSB_LAUNCH(flow_emit_cells_kernel, (unsigned)((igw + FE_WARPS - 1) / FE_WARPS), 32 * FE_WARPS, stream, cells, colcount, igw, igh,
                  d_entries, cap, d_count);
