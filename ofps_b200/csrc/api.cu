@@ -627,7 +627,12 @@ int ofpsb_interpolate_empty_cells(float* sums_xy, float* counts_xy, size_t w, si
         set_error("interpolate_empty_cells: invalid arguments");
         return OFPSB_E_INVALID;
     }
-    interpolate_empty_cells_host(sums_xy, counts_xy, w, h);
+    try {
+        interpolate_empty_cells_host(sums_xy, counts_xy, w, h);
+    } catch (const std::bad_alloc&) {   // no exception may cross the C ABI
+        set_error("interpolate_empty_cells: out of host memory (%zux%zu cells)", w, h);
+        return OFPSB_E_NOMEM;
+    }
     return OFPSB_OK;
 }
 
@@ -646,12 +651,17 @@ int ofpsb_flow_field(ofpsb_ctx* ctx, const ofps_mv* entries, size_t n, size_t w,
     if (int rc = launch_densify(ctx->d_entries.as<ofps_mv>(), n, w, h, ctx->d_field.as<float>(), ctx->d_counts.as<float>(),
                                 ctx->densify, ctx->stream, &ctx->launches, ctx->opt_densify_path, /*raw=*/1))
         return rc;
-    std::vector<float> counts(2 * cells);
-    OFPSB_CUDA_TRY(cudaMemcpyAsync(field_xy, ctx->d_field.ptr, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    OFPSB_CUDA_TRY(cudaMemcpyAsync(counts.data(), ctx->d_counts.ptr, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    OFPSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    interpolate_empty_cells_host(field_xy, counts.data(), w, h);
-    for (size_t i = 0; i < 2 * cells; i++) field_xy[i] = field_xy[i] / counts[i];   // MotionField::from (:297-308)
+    try {
+        std::vector<float> counts(2 * cells);
+        OFPSB_CUDA_TRY(cudaMemcpyAsync(field_xy, ctx->d_field.ptr, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        OFPSB_CUDA_TRY(cudaMemcpyAsync(counts.data(), ctx->d_counts.ptr, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        OFPSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        interpolate_empty_cells_host(field_xy, counts.data(), w, h);
+        for (size_t i = 0; i < 2 * cells; i++) field_xy[i] = field_xy[i] / counts[i];   // MotionField::from (:297-308)
+    } catch (const std::bad_alloc&) {   // no exception may cross the C ABI
+        set_error("flow_field: out of host memory (%zux%zu cells)", w, h);
+        return OFPSB_E_NOMEM;
+    }
     return OFPSB_OK;
 }
 
