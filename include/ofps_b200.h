@@ -240,7 +240,9 @@ int ofpsb_contrast_mask_dev(ofpsb_ctx *ctx, const uint8_t *d_gray, int w, int h,
  * (the first cap entries are still written). */
 int ofpsb_flow_entries(ofpsb_ctx *ctx, const float *flow_xy, const uint8_t *mask, int w, int h,
                        size_t gw, size_t gh, ofps_mv *entries, size_t cap, size_t *n);
-/* Device variant: strides in elements (floats / bytes); d_entries device memory; *n returned to host. */
+/* Device variant: strides in elements (floats / bytes); d_entries device memory, 16-byte aligned (cudaMalloc /
+ * ofpsb_dev_alloc pointers are); *n returned to host (one stream synchronisation).  16-byte aligned flow / mask rows
+ * (base and pitch) take the asynchronous-copy staging path, anything else the element-wise one. */
 int ofpsb_flow_entries_dev(ofpsb_ctx *ctx, const float *d_flow_xy, size_t flow_stride, const uint8_t *d_mask,
                            size_t mask_stride, int w, int h, size_t gw, size_t gh,
                            ofps_mv *d_entries, size_t cap, size_t *n);
