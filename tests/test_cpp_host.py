@@ -114,3 +114,17 @@ def test_motion_extract_matches_oracle(tmp_path, oracle):
     for i in range(3):
         want = oracle.block_match(frames[i], frames[i + 1], 16, 8, 0)[2]
         assert capi.mvec_read(out, i).tobytes() == want.tobytes(), i
+
+
+def test_flow_extract_compiles_and_refuses_cpu(tmp_path):
+    """tools/flow_extract.cpp (the reference's flow-extract on the C ABI) builds; without a GPU it stops at the context."""
+    import torch
+    exe = str(tmp_path / "flow_extract")
+    libdir = os.path.join(ROOT, "ofps_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tools", "flow_extract.cpp"), "-o", exe, "-L", libdir, "-lofps_b200",
+                           f"-Wl,-rpath,{libdir}"])
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p = subprocess.run([exe, str(tmp_path / "x.mvec"), str(tmp_path / "out"), "64", "48"], capture_output=True, text=True)
+    assert p.returncode == 3 and "no CPU fallback" in p.stderr
