@@ -367,6 +367,8 @@ int ofpsb_set_option(ofpsb_ctx* ctx, const char* key, long long value)
     else if (!strcmp(key, "batch_chunk_pairs") && value >= 0 && value <= 65535) ctx->opt_batch_chunk_pairs = (int)value;
     else if (!strcmp(key, "block_match_prune") && value >= 0 && value <= 1) ctx->opt_block_match_prune = (int)value;
     else if (!strcmp(key, "block_match_stats") && value >= 0 && value <= 1) ctx->bm_scratch.collect_stats = value != 0;
+    else if (!strcmp(key, "block_match_prefetch_tiles") && value >= -1 && value <= 1000000) ctx->bm_scratch.prefetch_tiles = (int)value;
+    else if (!strcmp(key, "block_match_pruner") && value >= 0 && value <= 1) ctx->bm_scratch.pruner = (int)value;
     else if (!strcmp(key, "block_match_chunk_pairs") && value >= 0 && value <= 32768) ctx->bm_scratch.chunk_pairs = (int)value;
     else {
         set_error("set_option: unknown key or value out of range: %s = %lld", key, value);

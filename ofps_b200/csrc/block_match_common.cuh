@@ -9,9 +9,13 @@ constexpr unsigned long long KEY_MAX = ~0ull;
 
 __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t acc)
 {
+#ifdef OFPSB_EMU
+    return __dp4a(__vabsdiffu4(a, b), 0x01010101u, acc);
+#else
     uint32_t r;
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(acc));
     return r;
+#endif
 }
 
 __device__ __forceinline__ uint32_t ssd4_acc(uint32_t a, uint32_t b, uint32_t acc)

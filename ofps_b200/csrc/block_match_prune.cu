@@ -221,7 +221,9 @@ __device__ __forceinline__ void prune_block(const uint16_t* __restrict__ sS, con
         c0 = *reinterpret_cast<const uint32_t*>(sC + (lane >> 1) * CW + wib * B + 4 * (lane & 1));
     }
     // the whole tile is interior when no candidate of any of its blocks leaves the frame (CTA-uniform)
-    const bool interior = dy_lo == -R && dy_hi == R && x0t - R >= 0 && x0t + (PRUNE_WARPS - 1) * B + R <= p.w - B && tile_full;
+    // (with ND < 32 the lanes beyond dx = +R must be masked: only the predicated path does that — ADVICE r1)
+    const bool interior = (HAS_EXTRA || ND % 32 == 0) && dy_lo == -R && dy_hi == R && x0t - R >= 0 &&
+                          x0t + (PRUNE_WARPS - 1) * B + R <= p.w - B && tile_full;
     const int col0 = wib * B + lane;   // column of dx = lane - R in the staged window
 
     // ---- pass 1: smallest bound key.  Per lane and column the dy fold uses key = lb << 7 | rank(dy)
@@ -458,9 +460,18 @@ static int pruned_chunk(const BlockMatchParams& p, BlockMatchScratch& sc, int sm
 // in chunks small enough to stay L2-resident ("block_match_chunk_pairs").  Measured on B200 (64 1080p pairs):
 // chunks of 4 / 8 / 16 / 32 / 64 pairs -> 20.1 / 17.1 / 15.7 / 14.6 / 14.3 us per pair: the path is bound by
 // instruction issue and TMA latency, not by HBM, and smaller launches only add tails — so the default is one chunk.
+int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int sm_count, cudaStream_t stream,
+                           uint64_t* launches);
+
 int launch_block_match_pruned(const BlockMatchParams& p, BlockMatchScratch& sc, int sm_count, cudaStream_t stream,
                               uint64_t* launches)
 {
+    // the fused four-term SEA kernel covers every tuned geometry up to +-16; +-32 keeps the round-1 pipeline
+    if (sc.pruner != 1) {
+        const int rc = launch_block_match_sea(p, sc, sm_count, stream, launches);
+        if (rc != 1) return rc;
+    }
+    if (p.range < 32 && sc.pruner != 1) return 1;
     int chunk = sc.chunk_pairs;
     if (chunk <= 0) chunk = p.n_pairs;
     if (chunk >= p.n_pairs) return pruned_chunk(p, sc, sm_count, stream, launches, true);

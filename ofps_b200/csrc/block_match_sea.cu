@@ -1,0 +1,647 @@
+// K1, default SAD path: fused multi-level successive elimination (SEA / MSEA, Li & Salari 1995, Gao et al. 2000).
+//
+// The exhaustive 16x16/+-16 SAD search is ~540 abs-diffs per input byte and is bound by the integer pipe, ~46x above
+// its HBM time.  The way towards the memory roofline that keeps the exhaustive-search RESULT is to not
+// evaluate candidates that provably cannot win.  With the block split into four sub-blocks of edge N = B/2,
+//     sum_k | sum(cur sub-block k) - sum(prev sub-window k) |   <=   SAD(cur block, prev window)
+// (triangle inequality per sub-block), so a candidate whose bound is not below the best exact cost found so far is out.
+// The four-term bound is what makes this work on real (noisy) content: on the noisy 1080p stream the 16x16 one-term
+// bound of round 1 left 237 of 1089 candidates per block alive, the four-term bound 4 (tools/sea_survivors.py).
+//
+// One CTA = one 128 x 64 pixel tile of blocks, one launch for the whole batch; nothing but the frames is read from
+// global memory and nothing but the results is written (round 1 wrote a u16 window-sum plane per frame to HBM and read it
+// back: 3.3x the algorithmic traffic):
+//   1. two TMA box loads: the previous-frame window of the tile (tile + R on every side; out-of-frame bytes arrive as
+//      zeros) and the current tile;
+//   2. the N x N window sums of every window position, in shared memory: one horizontal pass (dp4a on the staged words,
+//      four positions per thread) and one vertical sliding pass, in place (u16 pairs, no carries between the halves);
+//   3. one warp per block, a warp walks down a column of blocks:
+//        a. exact SAD of the zero vector and of a predictor (the winner of the block above; for the first block of a
+//           warp the candidate with the smallest bound of the tile's first block, found by the whole CTA);
+//        b. best cost 0: only a candidate with a SHORTER vector and bound 0 could still win -> scan the rows
+//           |dy| <= sqrt(d2 of the best) for window sums equal to the block's (one load + one compare per candidate);
+//        c. otherwise: the bounds of all (2R+1)^2 candidates into registers (lanes <-> dx: 2.5 shared loads + 4
+//           VABSDIFF per candidate), the candidate with the smallest bound is evaluated exactly, the candidates whose
+//           bound is still below the best are collected (bit masks, no ballots) and evaluated; more than SEA_CAP of
+//           them send the block to the work list of the exhaustive kernel (block_match_tma.cu).
+// Every comparison uses the spec's lexicographic key (cost, dx^2+dy^2, dy, dx), so the output is bit-identical to the
+// exhaustive kernels and to the oracle; only the amount of work is data-dependent.  Predictors change the work, never
+// the result: a candidate is dropped only when its (bound, position) key is not below an exact key already found.
+#ifndef OFPSB_EMU
+#include "tma_common.cuh"
+#else
+#include "block_match_common.cuh"
+#endif
+
+namespace ofpsb {
+
+namespace {
+
+using namespace bm;
+#ifndef OFPSB_EMU
+using namespace tma;
+#endif
+
+constexpr int SEA_WARPS = 8;
+constexpr int SEA_NT = SEA_WARPS * 32;
+constexpr int SEA_CAP = 32;                   // survivors a warp evaluates itself; more -> exhaustive work list
+constexpr uint32_t SEA_BIG = 0x00FFFFFFu;     // bound of an illegal candidate (real bounds are < 2^16)
+constexpr int SEA_TILE_W = 128, SEA_TILE_H = 64;
+
+template <int B, int R>
+struct SeaCfg {
+    static constexpr int N = B / 2;                       // sub-block edge
+    static constexpr int ND = 2 * R + 1;
+    static constexpr int TBX = SEA_TILE_W / B, TBY = SEA_TILE_H / B;
+    static constexpr int RA = (R + 15) & ~15;             // window origin on a 16-byte boundary (TMA, u8)
+    static constexpr int PW = SEA_TILE_W + 2 * RA;        // previous-frame window: bytes per row
+    static constexpr int PH = SEA_TILE_H + 2 * R;
+    static constexpr int CW = SEA_TILE_W, CH = SEA_TILE_H;
+    static constexpr int WC = PW / 2;                     // window-sum plane: u32 (= two u16 sums) per row
+    static constexpr int OR = PH - N + 1;                 // rows of window sums
+    static constexpr int NSEG = SEA_NT / WC;              // row segments of the vertical pass
+    static constexpr int SR = (OR + NSEG - 1) / NSEG;     // output rows per segment
+    static constexpr int HR = (NSEG * SR + N - 1) > PH ? (NSEG * SR + N - 1) : PH;   // plane rows incl. slack
+    static constexpr int P_BYTES = (PW * PH + 16 + 127) & ~127;   // +16: the last words read straddle the end
+    static constexpr int S_BYTES = (PW * 2 * HR + 127) & ~127;
+    static constexpr int C_BYTES = (CW * CH + 127) & ~127;
+    static constexpr int SMEM_BYTES = P_BYTES + S_BYTES + C_BYTES + 128;   // + alignment slack
+    static constexpr uint32_t TX_BYTES = (uint32_t)(PW * PH + CW * CH);
+    static constexpr bool EXTRA = ND > 32;                // column dx = +R is walked with lanes <-> dy
+    static constexpr int NL = EXTRA ? 32 : ND;            // lanes of the lanes <-> dx mapping (dx = lane - R)
+    static constexpr int NEX = EXTRA ? (ND + 31) / 32 : 0;
+    static constexpr int CPW = TBX / SEA_WARPS;           // block columns per warp
+    static_assert(B == 8 || B == 16, "sub-block sums are staged for 8x8 and 16x16 blocks");
+    static_assert(ND <= 33, "bounds of one dx column group live in registers");
+    static_assert(TBX % SEA_WARPS == 0 && PW % 16 == 0 && PW <= 256 && PH <= 256, "tile / TMA box limits");
+    static_assert(SR >= N && NSEG >= 1, "vertical pass: a segment is at least one window high");
+    static_assert(RA + B - R >= 2 * N, "every window-sum column a candidate reads is a full window");
+};
+
+__device__ __forceinline__ uint32_t sea_pos(int dx, int dy, int R)
+{
+    return ((uint32_t)(dx * dx + dy * dy) << 14) | ((uint32_t)(dy + R) << 7) | (uint32_t)(dx + R);
+}
+
+// ---- step 2: N x N window sums of the staged window, in shared memory ------------------------------------------------
+// horizontal: H[y][x] = sum of N bytes of row y starting at x, four x per thread from two / three aligned words
+template <int N, int PW, int PH>
+__device__ __forceinline__ void sea_hpass(const uint8_t* __restrict__ sP, uint32_t* __restrict__ sS, int tid)
+{
+    // one item = 16 consecutive positions of one row: one 16-byte load + the one / two words behind it
+    constexpr int IPR = PW / 16;
+    for (int item = tid; item < PH * IPR; item += SEA_NT) {
+        const int row = item / IPR, k = item - row * IPR;
+        const uint8_t* src = sP + row * PW + 16 * k;
+        const uint4 a = *reinterpret_cast<const uint4*>(src);
+        uint32_t w[6] = {a.x, a.y, a.z, a.w, 0u, 0u};
+        if (N == 8) {
+            const uint2 t = *reinterpret_cast<const uint2*>(src + 16);   // last item of the last row: the +16 slack
+            w[4] = t.x;
+            w[5] = t.y;
+        } else {
+            w[4] = *reinterpret_cast<const uint32_t*>(src + 16);
+        }
+        uint32_t m[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) m[j] = __dp4a(w[j], 0x01010101u, 0u);
+        uint32_t o[8];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            uint32_t h0, h1, h2, h3;
+            if (N == 8) {
+                h0 = m[g] + m[g + 1];
+                h1 = __dp4a(w[g], 0x01010100u, __dp4a(w[g + 2], 0x00000001u, m[g + 1]));
+                h2 = __dp4a(w[g], 0x01010000u, __dp4a(w[g + 2], 0x00000101u, m[g + 1]));
+                h3 = __dp4a(w[g], 0x01000000u, __dp4a(w[g + 2], 0x00010101u, m[g + 1]));
+            } else {
+                h0 = m[g];
+                h1 = __dp4a(w[g], 0x01010100u, __dp4a(w[g + 1], 0x00000001u, 0u));
+                h2 = __dp4a(w[g], 0x01010000u, __dp4a(w[g + 1], 0x00000101u, 0u));
+                h3 = __dp4a(w[g], 0x01000000u, __dp4a(w[g + 1], 0x00010101u, 0u));
+            }
+            o[2 * g] = h0 | (h1 << 16);
+            o[2 * g + 1] = h2 | (h3 << 16);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(sS + row * (PW / 2) + 8 * k);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// vertical, in place: S[y] = H[y] + ... + H[y+N-1] on u16 pairs (sums < 2^16: no carry or borrow crosses the halves).
+// A thread owns one u32 column of one row segment; the N-1 rows below its segment are read before anyone writes.
+template <typename C>
+__device__ __forceinline__ void sea_vpass(uint32_t* __restrict__ sS, int tid)
+{
+    constexpr int N = C::N, WC = C::WC, SR = C::SR;
+    const bool active = tid < C::NSEG * WC;
+    const int seg = tid / WC, col = tid - seg * WC;
+    uint32_t* base = sS + (seg * SR) * WC + col;
+    uint32_t tail[N - 1];
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < N - 1; j++) tail[j] = base[(SR + j) * WC];
+    }
+    __syncthreads();
+    if (active) {
+        uint32_t ring[N], v = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) { ring[j] = base[j * WC]; v += ring[j]; }
+#pragma unroll
+        for (int y = 0; y < SR; y++) {
+            base[y * WC] = v;
+            const uint32_t next = (y + N < SR) ? base[(y + N) * WC] : tail[(y + N - SR) < (N - 1) ? (y + N - SR) : 0];
+            v += next - ring[y % N];
+            ring[y % N] = next;
+        }
+    }
+}
+
+// Exact SAD of one candidate, one warp: 8 (B=16) or 4 (B=8) bytes of the block per lane, unaligned in x,
+// read from the staged previous-frame window (window coordinates wx, wy).
+template <int B, int PW>
+__device__ __forceinline__ uint32_t sea_exact(const uint8_t* __restrict__ win, int wx, int wy, uint32_t c0, uint32_t c1, int lane)
+{
+    uint32_t sad = 0;
+    if (B == 16) {
+        const int row = lane >> 1, xb = wx + 8 * (lane & 1);
+        const uint8_t* rp = win + (wy + row) * PW;
+        const int xa = xb & ~3, sh = (xb & 3) * 8;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(rp + xa);
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(rp + xa + 4);
+        const uint32_t w2 = *reinterpret_cast<const uint32_t*>(rp + xa + 8);   // only its low bytes are used
+        sad = sad4_acc(c0, __funnelshift_r(w0, w1, sh), 0);
+        sad = sad4_acc(c1, __funnelshift_r(w1, w2, sh), sad);
+    } else if (lane < 16) {   // B == 8: 16 lanes, one word each
+        const int row = lane >> 1, xb = wx + 4 * (lane & 1);
+        const uint8_t* rp = win + (wy + row) * PW;
+        const int xa = xb & ~3, sh = (xb & 3) * 8;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(rp + xa);
+        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(rp + xa + 4);
+        sad = sad4_acc(c0, __funnelshift_r(w0, w1, sh), 0);
+    }
+    return __reduce_add_sync(0xffffffffu, sad);
+}
+
+// K2: block winner -> outputs (av-decoder/src/lib.rs:404-419 convention; same operations as write_block_outputs,
+// with frame_norm = (1/W, 1/H) computed once per thread instead of once per block)
+template <int R>
+__device__ __forceinline__ void sea_write(const BlockMatchParams& p, size_t gb, uint32_t cost, uint32_t pos, int bx, int by,
+                                          float nx, float ny)
+{
+    const int dx = (int)(pos & 127u) - R, dy = (int)((pos >> 7) & 127u) - R;
+    if (p.mv_xy) *reinterpret_cast<uint32_t*>(p.mv_xy + 2 * gb) = ((uint32_t)dx & 0xFFFFu) | ((uint32_t)dy << 16);
+    if (p.cost) p.cost[gb] = cost;
+    if (p.entries) {
+        const int src_x = bx * p.block + p.block / 2 + dx;
+        const int src_y = p.y_offset + by * p.block + p.block / 2 + dy;
+        const float4 e = make_float4(__fmul_rn((float)src_x, nx), __fmul_rn((float)src_y, ny), __fmul_rn((float)dx, -nx),
+                                     __fmul_rn((float)dy, -ny));
+        *reinterpret_cast<float4*>(p.entries + gb) = e;
+    }
+}
+
+struct SeaOut {
+    uint32_t* worklist;
+    uint32_t* wl_count;
+    unsigned long long* stats;   // [0] blocks, [1] resolved here, [2] exact evaluations, [3] blocks that ran the full scan
+    float nx, ny;                // frame_norm = (1/W, 1/H), IEEE f32 divisions done once on the host
+    int prefetch_tiles;          // L2 prefetch distance in tiles (0 = off): about the number of resident CTAs
+};
+
+// current block -> registers (8 / 4 bytes per lane, lane = 2 * row + half) and its four sub-block sums -> every lane
+template <int B, int CW>
+__device__ __forceinline__ void sea_cur_block(const uint8_t* __restrict__ sC, int bxl, int byl, int lane, uint32_t& c0,
+                                              uint32_t& c1, uint32_t (&cs)[4])
+{
+    uint32_t part = 0;
+    c0 = c1 = 0;
+    if (B == 16) {
+        const uint2 v = *reinterpret_cast<const uint2*>(sC + (byl * B + (lane >> 1)) * CW + bxl * B + 8 * (lane & 1));
+        c0 = v.x;
+        c1 = v.y;
+        part = __dp4a(c0, 0x01010101u, __dp4a(c1, 0x01010101u, 0u));
+    } else if (lane < 16) {
+        c0 = *reinterpret_cast<const uint32_t*>(sC + (byl * B + (lane >> 1)) * CW + bxl * B + 4 * (lane & 1));
+        part = __dp4a(c0, 0x01010101u, 0u);
+    }
+    // B=16 -> sub-block (half, row >> 3): fold lanes that differ in bits 1..3; B=8 -> (half, row >> 2): bits 1..2
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    if (B == 16) part += __shfl_xor_sync(0xffffffffu, part, 8);
+    constexpr int LJ = B == 16 ? 16 : 8;                      // first lane of the lower sub-block row
+    cs[0] = __shfl_sync(0xffffffffu, part, 0);
+    cs[1] = __shfl_sync(0xffffffffu, part, 1);
+    cs[2] = __shfl_sync(0xffffffffu, part, LJ);
+    cs[3] = __shfl_sync(0xffffffffu, part, LJ + 1);
+}
+
+// ---- step 3: one block, one warp ------------------------------------------------------------------------------------
+// sS: window sums (u16, pitch PW), sP: previous-frame window, sC: current tile.  (bxl, byl): block inside the tile.
+// pred: position code of the predictor (0xFFFFFFFF = none).  Returns the winner's position code.
+template <int B, int R>
+__device__ __forceinline__ uint32_t sea_block(const uint16_t* __restrict__ sS, const uint8_t* __restrict__ sP,
+                                              const uint8_t* __restrict__ sC, const BlockMatchParams& p, int pair, int bx,
+                                              int by, int bxl, int byl, bool interior, uint32_t pred, int lane,
+                                              uint32_t* __restrict__ s_list, const SeaOut& out)
+{
+    using C = SeaCfg<B, R>;
+    constexpr int N = C::N, ND = C::ND, PW = C::PW, CW = C::CW;
+    const int x0 = bx * B, y0 = by * B;
+    const int dy_lo = max(-R, -p.halo_top - y0), dy_hi = min(R, p.strip_h + p.halo_bottom - B - y0);
+    const int dx_lo = max(-R, -x0), dx_hi = min(R, p.w - B - x0);
+    const int wx0 = bxl * B + C::RA, wy0 = byl * B + R;      // block origin in window coordinates
+    const int dx = lane - R;                                  // lanes <-> dx mapping
+    const bool lane_in = lane < C::NL && dx >= dx_lo && dx <= dx_hi;
+
+    uint32_t c0, c1, cs[4];
+    sea_cur_block<B, CW>(sC, bxl, byl, lane, c0, c1, cs);
+    const uint32_t C00 = cs[0], C10 = cs[1], C01 = cs[2], C11 = cs[3];
+
+    // ---- a. exact cost of the zero vector and of the predictor
+    const uint32_t pos00 = sea_pos(0, 0, R);
+    uint32_t bc = sea_exact<B, PW>(sP, wx0, wy0, c0, c1, lane), bp = pos00;
+    unsigned long long evaluated = 1;
+    uint32_t ppos = 0xFFFFFFFFu;
+    if (pred != 0xFFFFFFFFu && pred != pos00 && bc != 0) {
+        const int pdx = (int)(pred & 127u) - R, pdy = (int)((pred >> 7) & 127u) - R;
+        if (pdx >= dx_lo && pdx <= dx_hi && pdy >= dy_lo && pdy <= dy_hi) {
+            ppos = pred;
+            const uint32_t c = sea_exact<B, PW>(sP, wx0 + pdx, wy0 + pdy, c0, c1, lane);
+            evaluated++;
+            if (c < bc || (c == bc && pred < bp)) { bc = c; bp = pred; }
+        }
+    }
+    const uint16_t* scol = sS + byl * B * PW + wx0 - R + lane;   // window sum at (dx = lane - R, dy = -R)
+    bool resolved = true, full_scan = false;
+
+    if (bc == 0) {
+        // ---- b. a zero-cost match: only a zero-cost candidate with a smaller position code (a shorter vector) wins
+        if (bp != pos00) {
+            const int d2 = (int)(bp >> 14);
+            // rows that can hold a shorter vector: |dy| <= sqrt(d2) <= max + (min + 1) / 2 of (|dx|, |dy|) of the best
+            const int adx = abs((int)(bp & 127u) - R), ady = abs((int)((bp >> 7) & 127u) - R);
+            const int r = min(R, max(adx, ady) + ((min(adx, ady) + 1) >> 1));
+            const int ya = max(-r, dy_lo), yb = min(r, dy_hi);
+            const uint32_t c00l = lane_in ? C00 : 0xFFFFFFFFu;   // a window sum is < 2^16: idle lanes never match
+            // four rows per vote: one load + one compare per candidate; the other three sub-sums, the position test and
+            // the exact cost only where a first sub-sum matches (rows past yb are in the plane; they are skipped below)
+            const uint16_t* q4 = scol + (ya + R) * PW;
+            for (int dyq = ya; dyq <= yb; dyq += 4, q4 += 4 * PW) {
+                const bool any = ((uint32_t)q4[0] == c00l) | ((uint32_t)q4[PW] == c00l) | ((uint32_t)q4[2 * PW] == c00l) |
+                                 ((uint32_t)q4[3 * PW] == c00l);
+                if (__ballot_sync(0xffffffffu, any) == 0u) continue;
+#pragma unroll 1
+                for (int j = 0; j < 4 && dyq + j <= yb; j++) {
+                    const int dy = dyq + j;
+                    const uint16_t* q = q4 + j * PW;
+                    const bool h = (uint32_t)q[0] == c00l;
+                    if (__ballot_sync(0xffffffffu, h) == 0u) continue;
+                    const uint32_t pos = sea_pos(dx, dy, R);
+                    const bool zero = h && pos < bp && (uint32_t)q[N] == C10 && (uint32_t)q[N * PW] == C01 &&
+                                      (uint32_t)q[N * PW + N] == C11;
+                    unsigned m = __ballot_sync(0xffffffffu, zero);
+                    while (m) {
+                        const int l = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t cp = __shfl_sync(0xffffffffu, pos, l);
+                        if (cp >= bp) continue;
+                        const uint32_t c = sea_exact<B, PW>(sP, wx0 + l - R, wy0 + dy, c0, c1, lane);
+                        evaluated++;
+                        if (c == 0) bp = cp;
+                    }
+                }
+            }
+            if (C::EXTRA && R * R <= d2 && R <= dx_hi) {      // column dx = +R: lanes <-> dy
+#pragma unroll
+                for (int t = 0; t < (C::NEX > 0 ? C::NEX : 1); t++) {
+                    const int dyi = lane + 32 * t, dy = dyi - R;
+                    const bool ok = dyi < ND && dy >= dy_lo && dy <= dy_hi;
+                    const uint16_t* q = sS + (byl * B + (ok ? dyi : 0)) * PW + wx0 + R;
+                    const uint32_t pos = sea_pos(R, dy, R);
+                    const bool zero = ok && pos < bp && (uint32_t)q[0] == C00 && (uint32_t)q[N] == C10 &&
+                                      (uint32_t)q[N * PW] == C01 && (uint32_t)q[N * PW + N] == C11;
+                    unsigned m = __ballot_sync(0xffffffffu, zero);
+                    while (m) {
+                        const int l = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t cp = __shfl_sync(0xffffffffu, pos, l);
+                        if (cp >= bp) continue;
+                        const uint32_t c = sea_exact<B, PW>(sP, wx0 + R, wy0 + l + 32 * t - R, c0, c1, lane);
+                        evaluated++;
+                        if (c == 0) bp = cp;
+                    }
+                }
+            }
+        }
+    } else {
+        // ---- c. bounds of every candidate into registers: window-sum rows t = 0 .. ND+N-1, row t serves the upper
+        // sub-blocks of dy index t and the lower sub-blocks of dy index t-N
+        full_scan = true;
+        uint32_t b[ND];
+#pragma unroll
+        for (int t = 0; t < ND + N; t++) {
+            const uint32_t sa = scol[t * PW], sb = scol[t * PW + N];
+            if (t < ND) b[t] = __usad(sb, C10, __usad(sa, C00, 0u));
+            if (t >= N) b[t - N] = __usad(sb, C11, __usad(sa, C01, b[t - N]));
+        }
+        if (!interior) {
+#pragma unroll
+            for (int dyi = 0; dyi < ND; dyi++)
+                if (!lane_in || dyi - R < dy_lo || dyi - R > dy_hi) b[dyi] = SEA_BIG;
+        }
+        uint32_t bex[C::NEX > 0 ? C::NEX : 1];
+        if (C::EXTRA) {
+#pragma unroll
+            for (int t = 0; t < C::NEX; t++) {
+                const int dyi = lane + 32 * t, dy = dyi - R;
+                const bool ok = dyi < ND && dy >= dy_lo && dy <= dy_hi && R <= dx_hi;
+                const uint16_t* q = sS + (byl * B + (dyi < ND ? dyi : 0)) * PW + wx0 + R;
+                const uint32_t v = __usad(q[N * PW + N], C11, __usad(q[N * PW], C01, __usad(q[N], C10, __usad(q[0], C00, 0u))));
+                bex[t] = ok ? v : SEA_BIG;
+            }
+        }
+        // smallest (bound, position) key: per lane fold the dy of its column with key = bound << 7 | rank(dy)
+        uint32_t kmin = 0xFFFFFFFFu;
+#pragma unroll
+        for (int dyi = 0; dyi < ND; dyi++) {
+            const int dy = dyi - R;
+            kmin = min(kmin, b[dyi] * 128u + (uint32_t)(2 * (dy < 0 ? -dy : dy) - (dy < 0 ? 1 : 0)));
+        }
+        uint32_t my_lb = SEA_BIG, my_pos = 0xFFFFFFFFu;
+        if (lane < C::NL && (kmin >> 7) < SEA_BIG) {
+            const int code = (int)(kmin & 127u);
+            const int ady = (code + 1) >> 1;
+            my_lb = kmin >> 7;
+            my_pos = sea_pos(dx, (code & 1) ? -ady : ady, R);
+        }
+        if (C::EXTRA) {
+#pragma unroll
+            for (int t = 0; t < C::NEX; t++) {
+                const uint32_t pos = sea_pos(R, lane + 32 * t - R, R);
+                if (bex[t] < my_lb || (bex[t] == my_lb && bex[t] < SEA_BIG && pos < my_pos)) { my_lb = bex[t]; my_pos = pos; }
+            }
+        }
+        const uint32_t lb_min = __reduce_min_sync(0xffffffffu, my_lb);
+        const uint32_t pos_min = __reduce_min_sync(0xffffffffu, my_lb == lb_min ? my_pos : 0xFFFFFFFFu);
+        if (lb_min < bc || (lb_min == bc && pos_min < bp)) {
+            if (pos_min != pos00 && pos_min != ppos) {
+                const uint32_t c = sea_exact<B, PW>(sP, wx0 + (int)(pos_min & 127u) - R, wy0 + (int)((pos_min >> 7) & 127u) - R, c0, c1, lane);
+                evaluated++;
+                if (c < bc || (c == bc && pos_min < bp)) { bc = c; bp = pos_min; }
+            }
+            // candidates whose bound is not above the best cost: one bit per dy (ties are sorted out below)
+            uint32_t mlo = 0, mhi = 0;
+#pragma unroll
+            for (int dyi = 0; dyi < ND; dyi++) {
+                if (b[dyi] <= bc) {
+                    if (dyi < 32) mlo |= 1u << dyi;
+                    else mhi |= 1u << (dyi - 32);
+                }
+            }
+            if (lane >= C::NL) mlo = mhi = 0;
+            uint32_t mex = 0;
+            if (C::EXTRA) {
+#pragma unroll
+                for (int t = 0; t < C::NEX; t++)
+                    if (bex[t] <= bc) mex |= 1u << t;
+            }
+            const int mine = __popc(mlo) + __popc(mhi) + __popc(mex);
+            const int total = (int)__reduce_add_sync(0xffffffffu, (uint32_t)mine);
+            if (total > SEA_CAP) {
+                resolved = false;
+            } else {
+                // exclusive prefix of `mine` over the lanes -> slots of this lane's candidates
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = (int)__shfl_up_sync(0xffffffffu, (uint32_t)incl, o);
+                    if (lane >= o) incl += u;
+                }
+                int slot = incl - mine;
+                while (mlo) { const int dyi = __ffs(mlo) - 1; mlo &= mlo - 1; s_list[slot++] = ((uint32_t)dyi << 7) | (uint32_t)lane; }
+                while (mhi) { const int dyi = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; s_list[slot++] = ((uint32_t)dyi << 7) | (uint32_t)lane; }
+                while (mex) { const int t = __ffs(mex) - 1; mex &= mex - 1; s_list[slot++] = ((uint32_t)(lane + 32 * t) << 7) | (uint32_t)(2 * R); }
+                __syncwarp();
+                for (int i = 0; i < total; i++) {
+                    const uint32_t e = s_list[i];
+                    const int dxi = (int)(e & 127u), dyi = (int)(e >> 7);
+                    const uint32_t pos = sea_pos(dxi - R, dyi - R, R);
+                    if (pos == pos00 || pos == ppos || pos == pos_min) continue;   // already evaluated
+                    if (bc == 0 && pos > bp) continue;
+                    const uint16_t* q = sS + (byl * B + dyi) * PW + wx0 - R + dxi;
+                    const uint32_t lb = __usad(q[N * PW + N], C11, __usad(q[N * PW], C01, __usad(q[N], C10, __usad(q[0], C00, 0u))));
+                    if (!(lb < bc || (lb == bc && pos < bp))) continue;           // the best tightened meanwhile
+                    const uint32_t c = sea_exact<B, PW>(sP, wx0 + dxi - R, wy0 + dyi - R, c0, c1, lane);
+                    evaluated++;
+                    if (c < bc || (c == bc && pos < bp)) { bc = c; bp = pos; }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    if (lane == 0) {
+        const size_t gb = (size_t)((uint32_t)(pair * p.nby + by) * (uint32_t)p.nbx + (uint32_t)bx);   // < 2^32 (checked by the launcher)
+        if (resolved) {
+            sea_write<R>(p, gb, bc, bp, bx, by, out.nx, out.ny);
+        } else {
+            out.worklist[atomicAdd(out.wl_count, 1u)] = (uint32_t)gb;
+        }
+        if (out.stats) {
+            atomicAdd(&out.stats[0], 1ull);
+            atomicAdd(&out.stats[1], resolved ? 1ull : 0ull);
+            atomicAdd(&out.stats[2], evaluated);
+            atomicAdd(&out.stats[3], full_scan ? 1ull : 0ull);
+        }
+    }
+    return bp;
+}
+
+#ifdef OFPSB_EMU
+struct SeaMaps { int unused; };
+#else
+struct SeaMaps { CUtensorMap prev, cur; };
+#endif
+
+template <int B, int R>
+__global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ SeaMaps maps, const BlockMatchParams p,
+                                                        const SeaOut out)
+{
+    using C = SeaCfg<B, R>;
+    OFPSB_DYN_SMEM(smem);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_list[SEA_WARPS][SEA_CAP];
+    __shared__ uint32_t s_probe[SEA_WARPS];
+#ifndef OFPSB_EMU
+    uint8_t* sP = smem + ((128u - (smem_u32(smem) & 127u)) & 127u);   // TMA destinations: 128-byte aligned
+#else
+    uint8_t* sP = smem;
+#endif
+    uint32_t* sS32 = reinterpret_cast<uint32_t*>(sP + C::P_BYTES);
+    uint8_t* sC = sP + C::P_BYTES + C::S_BYTES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx0 = blockIdx.x * SEA_TILE_W, ty0 = blockIdx.y * SEA_TILE_H, pair = blockIdx.z;
+    const int wx = tx0 - C::RA, wy = ty0 + p.halo_top - R;   // tensor row 0 of prev = first halo row
+#ifndef OFPSB_EMU
+    if (tid == 0) {
+        const uint32_t b32 = smem_u32(&bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b32));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(C::TX_BYTES) : "memory");
+        tma_load_3d(smem_u32(sP), &maps.prev, wx, wy, pair, b32);
+        tma_load_3d(smem_u32(sC), &maps.cur, tx0, ty0, pair, b32);
+        // the frames stream through the L2 once: pull the boxes of the tile a CTA that starts about one wave later will
+        // load into the L2 now, so that its loads do not wait for HBM
+        if (out.prefetch_tiles > 0) {
+            const unsigned per_pair = gridDim.x * gridDim.y;
+            const unsigned t = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + (unsigned)out.prefetch_tiles;
+            const unsigned tz = t / per_pair, trem = t - tz * per_pair;
+            if (tz < gridDim.z) {
+                const int py = (int)(trem / gridDim.x), px = (int)(trem - (unsigned)py * gridDim.x);
+                tma_prefetch_3d(&maps.prev, px * SEA_TILE_W - C::RA, py * SEA_TILE_H + p.halo_top - R, (int)tz);
+                tma_prefetch_3d(&maps.cur, px * SEA_TILE_W, py * SEA_TILE_H, (int)tz);
+            }
+        }
+    }
+    __syncthreads();
+    mbar_wait(smem_u32(&bar), 0);
+#else
+    (void)maps;
+    (void)bar;
+    {   // stand-in for the two TMA box loads: out-of-tensor bytes are zeros
+        const int rows_prev = p.halo_top + p.strip_h + p.halo_bottom;
+        const uint8_t* pb = p.prev - (long long)p.halo_top * p.stride + (long long)pair * p.pair_stride;
+        const uint8_t* cb = p.cur + (long long)pair * p.pair_stride;
+        for (int i = tid; i < C::PW * C::PH; i += SEA_NT) {
+            const int y = wy + i / C::PW, x = wx + i % C::PW;
+            sP[i] = (x >= 0 && x < p.w && y >= 0 && y < rows_prev) ? pb[(long long)y * p.stride + x] : 0;
+        }
+        for (int i = tid; i < C::CW * C::CH; i += SEA_NT) {
+            const int y = ty0 + i / C::CW, x = tx0 + i % C::CW;
+            sC[i] = (x < p.w && y < p.strip_h) ? cb[(long long)y * p.stride + x] : 0;
+        }
+    }
+    __syncthreads();
+#endif
+    sea_hpass<C::N, C::PW, C::PH>(sP, sS32, tid);
+    __syncthreads();
+    sea_vpass<C>(sS32, tid);
+    __syncthreads();
+
+    // the whole tile is interior when no candidate of any of its blocks leaves the frame (CTA-uniform)
+    const bool interior = tx0 - R >= 0 && tx0 + SEA_TILE_W + R <= p.w && ty0 - R >= -p.halo_top &&
+                          ty0 + SEA_TILE_H + R <= p.strip_h + p.halo_bottom &&
+                          tx0 / B + C::TBX <= p.nbx && ty0 / B + C::TBY <= p.nby;
+    const uint16_t* sS = reinterpret_cast<const uint16_t*>(sS32);
+
+    // tile predictor: the candidate of the tile's first block with the smallest four-term bound, found by the whole CTA
+    // (a few candidates per thread).  It only seeds the first block of every warp — a predictor changes the work,
+    // never the result — and replaces a full scan per warp and tile (ncu: a quarter of all blocks before this).
+    {
+        constexpr int N = C::N, ND = C::ND, PW = C::PW;
+        uint32_t c0, c1, cs[4];
+        sea_cur_block<B, C::CW>(sC, 0, 0, lane, c0, c1, cs);
+        const int dy_lo = max(-R, -p.halo_top - ty0), dy_hi = min(R, p.strip_h + p.halo_bottom - B - ty0);
+        const int dx_lo = max(-R, -tx0), dx_hi = min(R, p.w - B - tx0);
+        uint32_t kb = 0xFFFFFFFFu;
+        for (int idx = tid; idx < ND * ND; idx += SEA_NT) {
+            const int dyi = idx / ND, dxi = idx - dyi * ND;
+            const uint16_t* q = sS + dyi * PW + C::RA - R + dxi;
+            const uint32_t v = __usad(q[N * PW + N], cs[3], __usad(q[N * PW], cs[2], __usad(q[N], cs[1], __usad(q[0], cs[0], 0u))));
+            const bool ok = dxi - R >= dx_lo && dxi - R <= dx_hi && dyi - R >= dy_lo && dyi - R <= dy_hi;
+            if (ok) kb = min(kb, (v << 12) | (uint32_t)idx);
+        }
+        kb = __reduce_min_sync(0xffffffffu, kb);
+        if (lane == 0) s_probe[warp] = kb;
+    }
+    __syncthreads();
+    uint32_t pred;
+    {
+        uint32_t kb = s_probe[0];
+#pragma unroll
+        for (int i = 1; i < SEA_WARPS; i++) kb = min(kb, s_probe[i]);
+        const int idx = (int)(kb & 4095u), dyi = idx / C::ND;
+        pred = sea_pos(idx - dyi * C::ND - R, dyi - R, R);
+    }
+    for (int it = 0; it < C::TBY * C::CPW; it++) {
+        const int byl = it / C::CPW, bxl = warp * C::CPW + it % C::CPW;
+        const int bx = tx0 / B + bxl, by = ty0 / B + byl;
+        if (bx >= p.nbx || by >= p.nby) continue;
+        pred = sea_block<B, R>(sS, sP, sC, p, pair, bx, by, bxl, byl, interior, pred, lane, s_list[warp], out);
+    }
+}
+
+#ifndef OFPSB_EMU
+template <int B, int R>
+int launch_sea(const BlockMatchParams& p, const SeaOut& out, cudaStream_t stream)
+{
+    using C = SeaCfg<B, R>;
+    const int rows_prev = p.halo_top + p.strip_h + p.halo_bottom;
+    const uint8_t* prev_base = p.prev - (long long)p.halo_top * p.stride;
+    SeaMaps maps;
+    if (!make_map(&maps.prev, prev_base, p.w, rows_prev, p.stride, p.pair_stride, p.n_pairs, C::PW, C::PH) ||
+        !make_map(&maps.cur, p.cur, p.w, p.strip_h, p.stride, p.pair_stride, p.n_pairs, C::CW, C::CH))
+        return 1;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    OFPSB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        OFPSB_CUDA_TRY(cudaFuncSetAttribute(sea_kernel<B, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const dim3 grid((p.nbx * B + SEA_TILE_W - 1) / SEA_TILE_W, (p.nby * B + SEA_TILE_H - 1) / SEA_TILE_H, p.n_pairs);
+    sea_kernel<B, R><<<grid, SEA_NT, C::SMEM_BYTES, stream>>>(maps, p, out);
+    OFPSB_CUDA_TRY(cudaGetLastError());
+    return OFPSB_OK;
+}
+#endif
+
+}  // namespace
+
+#ifndef OFPSB_EMU
+bool block_match_tma_usable(const BlockMatchParams& p);
+int launch_block_match_list(const BlockMatchParams& p, const uint32_t* d_list, const uint32_t* d_count, int sm_count,
+                            cudaStream_t stream);
+
+// Fused SEA search of one batch.  Returns 0 when launched, 1 when the path does not apply (metric, geometry,
+// alignment) — the caller then tries the other paths — and < 0 on error.
+int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int sm_count, cudaStream_t stream,
+                           uint64_t* launches)
+{
+    if (p.metric != OFPSB_METRIC_SAD || !block_match_tma_usable(p)) return 1;
+    const bool geom = (p.block == 16 || p.block == 8) && (p.range == 8 || p.range == 16);
+    if (!geom) return 1;
+    const int rows_prev = p.halo_top + p.strip_h + p.halo_bottom;
+    if (p.w < p.block || rows_prev < p.block) return 1;
+    const long long total = (long long)p.nbx * p.nby * p.n_pairs;
+    if (total >= 0xFFFFFFF0ll) return 1;
+    // scratch: [0] work-list count, [2..9] four 64-bit statistics, then the work list
+    const size_t head = 16;
+    if (int rc = sc.worklist.reserve((head + (size_t)total + 8) * sizeof(uint32_t))) return rc;
+    uint32_t* base = sc.worklist.as<uint32_t>();
+    SeaOut out;
+    out.wl_count = base;
+    out.stats = sc.collect_stats ? reinterpret_cast<unsigned long long*>(base + 2) : nullptr;
+    out.nx = 1.0f / (float)p.w;          // av-decoder/src/lib.rs:404-405 (host code is built with -ffp-contract=off)
+    out.ny = 1.0f / (float)p.full_h;
+    out.prefetch_tiles = sc.prefetch_tiles >= 0 ? sc.prefetch_tiles : 3 * (sm_count > 0 ? sm_count : 148);
+    out.worklist = base + head;
+    OFPSB_CUDA_TRY(cudaMemsetAsync(base, 0, head * sizeof(uint32_t), stream));
+    int rc = 1;
+    if (p.block == 16 && p.range == 16) rc = launch_sea<16, 16>(p, out, stream);
+    else if (p.block == 16 && p.range == 8) rc = launch_sea<16, 8>(p, out, stream);
+    else if (p.block == 8 && p.range == 16) rc = launch_sea<8, 16>(p, out, stream);
+    else if (p.block == 8 && p.range == 8) rc = launch_sea<8, 8>(p, out, stream);
+    if (rc) return rc;
+    rc = launch_block_match_list(p, out.worklist, out.wl_count, sm_count, stream);
+    if (rc != OFPSB_OK) {
+        set_error("block_match: work-list kernel unavailable for block=%d range=%d", p.block, p.range);
+        return rc < 0 ? rc : OFPSB_E_INVALID;
+    }
+    if (launches) *launches += 2;
+    return OFPSB_OK;
+}
+#endif
+
+}  // namespace ofpsb

@@ -78,6 +78,8 @@ int launch_block_match(const BlockMatchParams& p, cudaStream_t stream, uint64_t*
 struct BlockMatchScratch {
     DevBuf sums, worklist;
     bool collect_stats = false;
+    int prefetch_tiles = -1;  // SEA kernel: L2 prefetch distance in tiles (-1 = three CTAs per SM, 0 = off)
+    int pruner = 0;           // 0 = fused SEA kernel where it applies (default), 1 = round-1 window-sum pipeline (tests / A-B)
     int chunk_pairs = 0;      // pairs per pruned chunk (0 = whole batch; smaller chunks stay L2-resident but measured slower)
     size_t l2_bytes = 0;
 };

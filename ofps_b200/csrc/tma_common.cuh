@@ -19,6 +19,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// L2 prefetch of a box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t b32, uint32_t parity)
 {
     uint32_t done = 0;
@@ -32,16 +38,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t b32, uint32_t parity)
 
 inline PFN_cuTensorMapEncodeTiled get_encode()
 {
-    static PFN_cuTensorMapEncodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // C++11 magic static: initialised exactly once even when contexts live on different host threads
+    static const PFN_cuTensorMapEncodeTiled fn = [] {
         void* ptr = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(ptr);
-    }
+            return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(ptr);
+        return static_cast<PFN_cuTensorMapEncodeTiled>(nullptr);
+    }();
     return fn;
 }
 

@@ -131,10 +131,12 @@ def make_batch(n_pairs: int, w: int, h: int, search: int, noise_lsb: int = 0, fi
 
 
 def make_stream(n_frames: int, w: int, h: int, search: int, n_rects: int = 8, seed: int = BASE_SEED,
-                first_index: int = 0) -> np.ndarray:
+                first_index: int = 0, noise_lsb: int = 0) -> np.ndarray:
     """``n_frames`` consecutive luma frames [n, h, w] of one synthetic video: frame i+1 is frame i
     panned by an integer global motion with ``n_rects`` rectangles moved on their own (the
-    :func:`make_pair` recipe, chained), so pair (i, i+1) is a real motion pair for every i."""
+    :func:`make_pair` recipe, chained), so pair (i, i+1) is a real motion pair for every i.
+    ``noise_lsb`` > 0 adds independent uniform sensor noise in [-noise_lsb, noise_lsb] to every frame
+    (the clean content is what is chained, so the noise does not accumulate): no pair has an exact match."""
     rng = _Rng(seed + 7919 * (first_index + 1))
     frames = np.empty((n_frames, h, w), np.uint8)
     frames[0] = textured_plane(rng.next(), w, h)
@@ -155,6 +157,11 @@ def make_stream(n_frames: int, w: int, h: int, search: int, n_rects: int = 8, se
             if cx1 > cx0 and cy1 > cy0:
                 cur[cy0:cy1, cx0:cx1] = prev[cy0 - dy:cy1 - dy, cx0 - dx:cx1 - dx]
         frames[i] = cur
+    if noise_lsb > 0:
+        nrng = _Rng(seed ^ 0x5EED0000 ^ (first_index + 1))
+        for i in range(n_frames):
+            nz = noise_plane(nrng.next(), w, h).astype(np.int16) % (2 * noise_lsb + 1) - noise_lsb
+            frames[i] = np.clip(frames[i].astype(np.int16) + nz, 0, 255).astype(np.uint8)
     return frames
 
 

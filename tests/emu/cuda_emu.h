@@ -157,6 +157,23 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((unsigned long long)hi << 32) | lo) >> (sh & 31)); }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline uint32_t __dp4a(uint32_t a, uint32_t b, uint32_t c)
+{
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 255u) * ((b >> (8 * i)) & 255u);
+    return c;
+}
+inline uint32_t __usad(uint32_t a, uint32_t b, uint32_t c) { return c + (a > b ? a - b : b - a); }
+inline uint32_t __vabsdiffu4(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        const int x = (int)((a >> (8 * i)) & 255u), y = (int)((b >> (8 * i)) & 255u);
+        r |= (uint32_t)(x > y ? x - y : y - x) << (8 * i);
+    }
+    return r;
+}
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 using std::max;
 using std::min;
 

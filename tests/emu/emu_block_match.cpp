@@ -1,0 +1,49 @@
+// TEST INFRASTRUCTURE — runs the fused SEA block-matching kernel of ofps_b200/csrc/block_match_sea.cu on the CPU
+// stand-in of tests/emu/cuda_emu.h (the two TMA box loads are replaced by plain copies with zero fill, everything
+// after them is the product code, unmodified), so that its logic — window sums, bounds, tie-breaks, predictor and
+// work-list decisions — can be checked against the oracle on the GPU-less build container.  Not shipped.
+#define OFPSB_EMU 1
+#include "../../ofps_b200/csrc/block_match_sea.cu"
+
+namespace ofpsb {
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    fputc('\n', stderr);
+    va_end(ap);
+}
+}  // namespace ofpsb
+
+using namespace ofpsb;
+
+extern "C" {
+// One strip (or whole frame: halo_top = halo_bottom = y_offset = 0, full_h = strip_h) of n_pairs pairs.
+// worklist: capacity nbx*nby*n_pairs; *wl_count receives the number of blocks the kernel left to the exhaustive search
+// (their outputs are untouched).  stats: 4 x u64.  use_hint: enable the batch-wide predictor.
+int emu_block_match_sea(const uint8_t* prev, const uint8_t* cur, int w, int strip_h, int stride, long long pair_stride,
+                        int n_pairs, int halo_top, int halo_bottom, int y_offset, int full_h, int block, int range,
+                        int16_t* mv, uint32_t* cost, ofps_mv* entries, uint32_t* worklist, uint32_t* wl_count,
+                        unsigned long long* stats, int use_hint)
+{
+    BlockMatchParams p{};
+    p.prev = prev; p.cur = cur; p.w = w; p.strip_h = strip_h; p.stride = stride; p.pair_stride = pair_stride;
+    p.n_pairs = n_pairs; p.halo_top = halo_top; p.halo_bottom = halo_bottom; p.y_offset = y_offset; p.full_h = full_h;
+    p.block = block; p.range = range; p.metric = OFPSB_METRIC_SAD; p.nbx = w / block; p.nby = strip_h / block;
+    p.mv_xy = mv; p.cost = cost; p.entries = entries;
+    (void)use_hint;
+    SeaOut out;
+    out.worklist = worklist; out.wl_count = wl_count; out.stats = stats;
+    out.nx = 1.0f / (float)w; out.ny = 1.0f / (float)full_h; out.prefetch_tiles = 0;
+    *wl_count = 0;
+    const dim3 grid((p.nbx * block + SEA_TILE_W - 1) / SEA_TILE_W, (p.nby * block + SEA_TILE_H - 1) / SEA_TILE_H, n_pairs);
+    SeaMaps maps{};
+    if (block == 16 && range == 16) OFPSB_LAUNCH_SMEM((sea_kernel<16, 16>), grid, SEA_NT, 0, nullptr, maps, p, out);
+    else if (block == 16 && range == 8) OFPSB_LAUNCH_SMEM((sea_kernel<16, 8>), grid, SEA_NT, 0, nullptr, maps, p, out);
+    else if (block == 8 && range == 16) OFPSB_LAUNCH_SMEM((sea_kernel<8, 16>), grid, SEA_NT, 0, nullptr, maps, p, out);
+    else if (block == 8 && range == 8) OFPSB_LAUNCH_SMEM((sea_kernel<8, 8>), grid, SEA_NT, 0, nullptr, maps, p, out);
+    else return 1;
+    return 0;
+}
+}
