@@ -210,44 +210,60 @@ struct SeaOut {
     int prefetch_tiles;          // L2 prefetch distance in tiles (0 = off): about the number of resident CTAs
 };
 
-// current block -> registers (8 / 4 bytes per lane, lane = 2 * row + half) and its four sub-block sums -> every lane
+// current block -> registers: 8 (B=16) / 4 (B=8, lanes 0..15) bytes per lane, lane = 2 * row + half
 template <int B, int CW>
 __device__ __forceinline__ void sea_cur_block(const uint8_t* __restrict__ sC, int bxl, int byl, int lane, uint32_t& c0,
-                                              uint32_t& c1, uint32_t (&cs)[4])
+                                              uint32_t& c1)
 {
-    uint32_t part = 0;
     c0 = c1 = 0;
     if (B == 16) {
         const uint2 v = *reinterpret_cast<const uint2*>(sC + (byl * B + (lane >> 1)) * CW + bxl * B + 8 * (lane & 1));
         c0 = v.x;
         c1 = v.y;
-        part = __dp4a(c0, 0x01010101u, __dp4a(c1, 0x01010101u, 0u));
     } else if (lane < 16) {
         c0 = *reinterpret_cast<const uint32_t*>(sC + (byl * B + (lane >> 1)) * CW + bxl * B + 4 * (lane & 1));
-        part = __dp4a(c0, 0x01010101u, 0u);
     }
-    // B=16 -> sub-block (half, row >> 3): fold lanes that differ in bits 1..3; B=8 -> (half, row >> 2): bits 1..2
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    part += __shfl_xor_sync(0xffffffffu, part, 4);
-    if (B == 16) part += __shfl_xor_sync(0xffffffffu, part, 8);
-    constexpr int LJ = B == 16 ? 16 : 8;                      // first lane of the lower sub-block row
-    cs[0] = __shfl_sync(0xffffffffu, part, 0);
-    cs[1] = __shfl_sync(0xffffffffu, part, 1);
-    cs[2] = __shfl_sync(0xffffffffu, part, LJ);
-    cs[3] = __shfl_sync(0xffffffffu, part, LJ + 1);
 }
+
+// the four N x N sub-block sums of every block of the current tile -> s_csum[block] = (C00, C10, C01, C11)
+template <typename C, int B>
+__device__ __forceinline__ void sea_cur_sums(const uint8_t* __restrict__ sC, uint32_t* __restrict__ s_csum, int tid)
+{
+    constexpr int N = C::N;
+    for (int i = tid; i < 4 * C::TBX * C::TBY; i += SEA_NT) {
+        const int blk = i >> 2, k = i & 3, bxl = blk % C::TBX, byl = blk / C::TBX;
+        const uint8_t* src = sC + (byl * B + (k >> 1) * N) * C::CW + bxl * B + (k & 1) * N;
+        uint32_t v = 0;
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+            if (N == 8) {
+                const uint2 w = *reinterpret_cast<const uint2*>(src + r * C::CW);
+                v = __dp4a(w.x, 0x01010101u, __dp4a(w.y, 0x01010101u, v));
+            } else {
+                v = __dp4a(*reinterpret_cast<const uint32_t*>(src + r * C::CW), 0x01010101u, v);
+            }
+        }
+        s_csum[i] = v;
+    }
+}
+
+struct SeaResult {   // per-block result, kept by lane `it` of the warp until the tile is written out
+    uint32_t cost, pos;
+    bool resolved;
+};
 
 // ---- step 3: one block, one warp ------------------------------------------------------------------------------------
 // sS: window sums (u16, pitch PW), sP: previous-frame window, sC: current tile.  (bxl, byl): block inside the tile.
-// pred: position code of the predictor (0xFFFFFFFF = none).  Returns the winner's position code.
+// pred: position code of the predictor.  Returns the winner (or, unresolved, the best found so far).
 template <int B, int R>
-__device__ __forceinline__ uint32_t sea_block(const uint16_t* __restrict__ sS, const uint8_t* __restrict__ sP,
-                                              const uint8_t* __restrict__ sC, const BlockMatchParams& p, int pair, int bx,
-                                              int by, int bxl, int byl, bool interior, uint32_t pred, int lane,
-                                              uint32_t* __restrict__ s_list, const SeaOut& out)
+__device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, const uint8_t* __restrict__ sP,
+                                               const uint8_t* __restrict__ sC, const uint32_t* __restrict__ s_csum,
+                                               const BlockMatchParams& p, int bx, int by, int bxl, int byl, bool interior,
+                                               uint32_t pred, int lane, uint32_t* __restrict__ s_list, const SeaOut& out)
 {
     using C = SeaCfg<B, R>;
     constexpr int N = C::N, ND = C::ND, PW = C::PW, CW = C::CW;
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
     const int x0 = bx * B, y0 = by * B;
     const int dy_lo = max(-R, -p.halo_top - y0), dy_hi = min(R, p.strip_h + p.halo_bottom - B - y0);
     const int dx_lo = max(-R, -x0), dx_hi = min(R, p.w - B - x0);
@@ -255,23 +271,27 @@ __device__ __forceinline__ uint32_t sea_block(const uint16_t* __restrict__ sS, c
     const int dx = lane - R;                                  // lanes <-> dx mapping
     const bool lane_in = lane < C::NL && dx >= dx_lo && dx <= dx_hi;
 
-    uint32_t c0, c1, cs[4];
-    sea_cur_block<B, CW>(sC, bxl, byl, lane, c0, c1, cs);
-    const uint32_t C00 = cs[0], C10 = cs[1], C01 = cs[2], C11 = cs[3];
+    uint32_t c0, c1;
+    sea_cur_block<B, CW>(sC, bxl, byl, lane, c0, c1);
+    const uint4 csum = *reinterpret_cast<const uint4*>(s_csum + 4 * (byl * C::TBX + bxl));
+    const uint32_t C00 = csum.x, C10 = csum.y, C01 = csum.z, C11 = csum.w;
 
-    // ---- a. exact cost of the zero vector and of the predictor
+    // ---- a. exact cost of the predictor; of the zero vector too unless the predictor already matches exactly (the
+    // zero vector is then one of the shorter candidates step b rules out by their window sums)
     const uint32_t pos00 = sea_pos(0, 0, R);
-    uint32_t bc = sea_exact<B, PW>(sP, wx0, wy0, c0, c1, lane), bp = pos00;
-    unsigned long long evaluated = 1;
-    uint32_t ppos = 0xFFFFFFFFu;
-    if (pred != 0xFFFFFFFFu && pred != pos00 && bc != 0) {
+    {
         const int pdx = (int)(pred & 127u) - R, pdy = (int)((pred >> 7) & 127u) - R;
-        if (pdx >= dx_lo && pdx <= dx_hi && pdy >= dy_lo && pdy <= dy_hi) {
-            ppos = pred;
-            const uint32_t c = sea_exact<B, PW>(sP, wx0 + pdx, wy0 + pdy, c0, c1, lane);
-            evaluated++;
-            if (c < bc || (c == bc && pred < bp)) { bc = c; bp = pred; }
-        }
+        if (pdx < dx_lo || pdx > dx_hi || pdy < dy_lo || pdy > dy_hi) pred = pos00;
+    }
+    uint32_t bc = sea_exact<B, PW>(sP, wx0 + (int)(pred & 127u) - R, wy0 + (int)((pred >> 7) & 127u) - R, c0, c1, lane);
+    uint32_t bp = pred;
+    unsigned long long evaluated = 1;
+    uint32_t zpos = pred == pos00 ? pos00 : NONE;             // pos00 once the zero vector has been evaluated
+    if (bc != 0 && pred != pos00) {
+        const uint32_t c = sea_exact<B, PW>(sP, wx0, wy0, c0, c1, lane);
+        evaluated++;
+        zpos = pos00;
+        if (c < bc || (c == bc && pos00 < bp)) { bc = c; bp = pos00; }
     }
     const uint16_t* scol = sS + byl * B * PW + wx0 - R + lane;   // window sum at (dx = lane - R, dy = -R)
     bool resolved = true, full_scan = false;
@@ -280,26 +300,36 @@ __device__ __forceinline__ uint32_t sea_block(const uint16_t* __restrict__ sS, c
         // ---- b. a zero-cost match: only a zero-cost candidate with a smaller position code (a shorter vector) wins
         if (bp != pos00) {
             const int d2 = (int)(bp >> 14);
+            const int bdx = (int)(bp & 127u) - R, bdy = (int)((bp >> 7) & 127u) - R;
             // rows that can hold a shorter vector: |dy| <= sqrt(d2) <= max + (min + 1) / 2 of (|dx|, |dy|) of the best
-            const int adx = abs((int)(bp & 127u) - R), ady = abs((int)((bp >> 7) & 127u) - R);
+            const int adx = abs(bdx), ady = abs(bdy);
             const int r = min(R, max(adx, ady) + ((min(adx, ady) + 1) >> 1));
             const int ya = max(-r, dy_lo), yb = min(r, dy_hi);
-            const uint32_t c00l = lane_in ? C00 : 0xFFFFFFFFu;   // a window sum is < 2^16: idle lanes never match
-            // four rows per vote: one load + one compare per candidate; the other three sub-sums, the position test and
-            // the exact cost only where a first sub-sum matches (rows past yb are in the plane; they are skipped below)
-            const uint16_t* q4 = scol + (ya + R) * PW;
-            for (int dyq = ya; dyq <= yb; dyq += 4, q4 += 4 * PW) {
-                const bool any = ((uint32_t)q4[0] == c00l) | ((uint32_t)q4[PW] == c00l) | ((uint32_t)q4[2 * PW] == c00l) |
-                                 ((uint32_t)q4[3 * PW] == c00l);
+            const uint32_t c00l = lane_in ? C00 : NONE;       // a window sum is < 2^16: idle lanes never match
+            // G rows per vote: one load + one compare per candidate; the other three sub-sums, the position test and
+            // the exact cost only where a first sub-sum matches.  Rows past yb are inside the plane (G - 1 <= N) and
+            // are masked below; the best's own position always matches and is masked too.
+            constexpr int G = N >= 8 ? 8 : 4;
+            const uint16_t* qg = scol + (ya + R) * PW;
+            for (int dyq = ya; dyq <= yb; dyq += G, qg += G * PW) {
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < G; j++) any |= (uint32_t)qg[j * PW] == c00l;
                 if (__ballot_sync(0xffffffffu, any) == 0u) continue;
-#pragma unroll 1
-                for (int j = 0; j < 4 && dyq + j <= yb; j++) {
+                uint32_t code = 0;
+#pragma unroll
+                for (int j = 0; j < G; j++) code |= ((uint32_t)qg[j * PW] == c00l ? 1u : 0u) << j;
+                const int nrow = yb - dyq + 1;
+                if (nrow < G) code &= (1u << nrow) - 1u;
+                if (dx == bdx && bdy >= dyq && bdy < dyq + G) code &= ~(1u << (bdy - dyq));
+                unsigned rows = __reduce_or_sync(0xffffffffu, code);
+                while (rows) {
+                    const int j = __ffs(rows) - 1;
+                    rows &= rows - 1;
                     const int dy = dyq + j;
-                    const uint16_t* q = q4 + j * PW;
-                    const bool h = (uint32_t)q[0] == c00l;
-                    if (__ballot_sync(0xffffffffu, h) == 0u) continue;
+                    const uint16_t* q = qg + j * PW;
                     const uint32_t pos = sea_pos(dx, dy, R);
-                    const bool zero = h && pos < bp && (uint32_t)q[N] == C10 && (uint32_t)q[N * PW] == C01 &&
+                    const bool zero = ((code >> j) & 1u) && pos < bp && (uint32_t)q[N] == C10 && (uint32_t)q[N * PW] == C01 &&
                                       (uint32_t)q[N * PW + N] == C11;
                     unsigned m = __ballot_sync(0xffffffffu, zero);
                     while (m) {
@@ -369,7 +399,7 @@ __device__ __forceinline__ uint32_t sea_block(const uint16_t* __restrict__ sS, c
             const int dy = dyi - R;
             kmin = min(kmin, b[dyi] * 128u + (uint32_t)(2 * (dy < 0 ? -dy : dy) - (dy < 0 ? 1 : 0)));
         }
-        uint32_t my_lb = SEA_BIG, my_pos = 0xFFFFFFFFu;
+        uint32_t my_lb = SEA_BIG, my_pos = NONE;
         if (lane < C::NL && (kmin >> 7) < SEA_BIG) {
             const int code = (int)(kmin & 127u);
             const int ady = (code + 1) >> 1;
@@ -384,9 +414,9 @@ __device__ __forceinline__ uint32_t sea_block(const uint16_t* __restrict__ sS, c
             }
         }
         const uint32_t lb_min = __reduce_min_sync(0xffffffffu, my_lb);
-        const uint32_t pos_min = __reduce_min_sync(0xffffffffu, my_lb == lb_min ? my_pos : 0xFFFFFFFFu);
+        const uint32_t pos_min = __reduce_min_sync(0xffffffffu, my_lb == lb_min ? my_pos : NONE);
         if (lb_min < bc || (lb_min == bc && pos_min < bp)) {
-            if (pos_min != pos00 && pos_min != ppos) {
+            if (pos_min != zpos && pos_min != pred) {
                 const uint32_t c = sea_exact<B, PW>(sP, wx0 + (int)(pos_min & 127u) - R, wy0 + (int)((pos_min >> 7) & 127u) - R, c0, c1, lane);
                 evaluated++;
                 if (c < bc || (c == bc && pos_min < bp)) { bc = c; bp = pos_min; }
@@ -428,7 +458,7 @@ __device__ __forceinline__ uint32_t sea_block(const uint16_t* __restrict__ sS, c
                     const uint32_t e = s_list[i];
                     const int dxi = (int)(e & 127u), dyi = (int)(e >> 7);
                     const uint32_t pos = sea_pos(dxi - R, dyi - R, R);
-                    if (pos == pos00 || pos == ppos || pos == pos_min) continue;   // already evaluated
+                    if (pos == zpos || pos == pred || pos == pos_min) continue;   // already evaluated
                     if (bc == 0 && pos > bp) continue;
                     const uint16_t* q = sS + (byl * B + dyi) * PW + wx0 - R + dxi;
                     const uint32_t lb = __usad(q[N * PW + N], C11, __usad(q[N * PW], C01, __usad(q[N], C10, __usad(q[0], C00, 0u))));
@@ -441,21 +471,17 @@ __device__ __forceinline__ uint32_t sea_block(const uint16_t* __restrict__ sS, c
             }
         }
     }
-    if (lane == 0) {
-        const size_t gb = (size_t)((uint32_t)(pair * p.nby + by) * (uint32_t)p.nbx + (uint32_t)bx);   // < 2^32 (checked by the launcher)
-        if (resolved) {
-            sea_write<R>(p, gb, bc, bp, bx, by, out.nx, out.ny);
-        } else {
-            out.worklist[atomicAdd(out.wl_count, 1u)] = (uint32_t)gb;
-        }
-        if (out.stats) {
-            atomicAdd(&out.stats[0], 1ull);
-            atomicAdd(&out.stats[1], resolved ? 1ull : 0ull);
-            atomicAdd(&out.stats[2], evaluated);
-            atomicAdd(&out.stats[3], full_scan ? 1ull : 0ull);
-        }
+    if (out.stats && lane == 0) {
+        atomicAdd(&out.stats[0], 1ull);
+        atomicAdd(&out.stats[1], resolved ? 1ull : 0ull);
+        atomicAdd(&out.stats[2], evaluated);
+        atomicAdd(&out.stats[3], full_scan ? 1ull : 0ull);
     }
-    return bp;
+    SeaResult res;
+    res.cost = bc;
+    res.pos = bp;
+    res.resolved = resolved;
+    return res;
 }
 
 #ifdef OFPSB_EMU
@@ -473,6 +499,7 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t s_list[SEA_WARPS][SEA_CAP];
     __shared__ uint32_t s_probe[SEA_WARPS];
+    __shared__ __align__(16) uint32_t s_csum[4 * C::TBX * C::TBY];
 #ifndef OFPSB_EMU
     uint8_t* sP = smem + ((128u - (smem_u32(smem) & 127u)) & 127u);   // TMA destinations: 128-byte aligned
 #else
@@ -525,6 +552,7 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
     __syncthreads();
 #endif
     sea_hpass<C::N, C::PW, C::PH>(sP, sS32, tid);
+    sea_cur_sums<C, B>(sC, s_csum, tid);
     __syncthreads();
     sea_vpass<C>(sS32, tid);
     __syncthreads();
@@ -540,16 +568,15 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
     // never the result — and replaces a full scan per warp and tile (ncu: a quarter of all blocks before this).
     {
         constexpr int N = C::N, ND = C::ND, PW = C::PW;
-        uint32_t c0, c1, cs[4];
-        sea_cur_block<B, C::CW>(sC, 0, 0, lane, c0, c1, cs);
+        const uint4 cs = *reinterpret_cast<const uint4*>(s_csum);
         const int dy_lo = max(-R, -p.halo_top - ty0), dy_hi = min(R, p.strip_h + p.halo_bottom - B - ty0);
         const int dx_lo = max(-R, -tx0), dx_hi = min(R, p.w - B - tx0);
         uint32_t kb = 0xFFFFFFFFu;
         for (int idx = tid; idx < ND * ND; idx += SEA_NT) {
             const int dyi = idx / ND, dxi = idx - dyi * ND;
             const uint16_t* q = sS + dyi * PW + C::RA - R + dxi;
-            const uint32_t v = __usad(q[N * PW + N], cs[3], __usad(q[N * PW], cs[2], __usad(q[N], cs[1], __usad(q[0], cs[0], 0u))));
-            const bool ok = dxi - R >= dx_lo && dxi - R <= dx_hi && dyi - R >= dy_lo && dyi - R <= dy_hi;
+            const uint32_t v = __usad(q[N * PW + N], cs.w, __usad(q[N * PW], cs.z, __usad(q[N], cs.y, __usad(q[0], cs.x, 0u))));
+            const bool ok = interior || (dxi - R >= dx_lo && dxi - R <= dx_hi && dyi - R >= dy_lo && dyi - R <= dy_hi);
             if (ok) kb = min(kb, (v << 12) | (uint32_t)idx);
         }
         kb = __reduce_min_sync(0xffffffffu, kb);
@@ -564,11 +591,30 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
         const int idx = (int)(kb & 4095u), dyi = idx / C::ND;
         pred = sea_pos(idx - dyi * C::ND - R, dyi - R, R);
     }
-    for (int it = 0; it < C::TBY * C::CPW; it++) {
+    // the warp's blocks; lane `it` keeps the result of block `it` and writes it after the loop (one pass of the output
+    // code per warp instead of one per block)
+    constexpr int NBW = C::TBY * C::CPW;
+    static_assert(NBW <= 32, "one lane per block of the warp");
+    uint32_t r_cost = 0, r_pos = 0;
+    int r_state = 0;   // 0 = no block, 1 = resolved, 2 = exhaustive work list
+    for (int it = 0; it < NBW; it++) {
         const int byl = it / C::CPW, bxl = warp * C::CPW + it % C::CPW;
         const int bx = tx0 / B + bxl, by = ty0 / B + byl;
         if (bx >= p.nbx || by >= p.nby) continue;
-        pred = sea_block<B, R>(sS, sP, sC, p, pair, bx, by, bxl, byl, interior, pred, lane, s_list[warp], out);
+        const SeaResult res = sea_block<B, R>(sS, sP, sC, s_csum, p, bx, by, bxl, byl, interior, pred, lane, s_list[warp], out);
+        pred = res.pos;
+        if (lane == it) {
+            r_cost = res.cost;
+            r_pos = res.pos;
+            r_state = res.resolved ? 1 : 2;
+        }
+    }
+    if (r_state) {
+        const int byl = lane / C::CPW, bxl = warp * C::CPW + lane % C::CPW;
+        const int bx = tx0 / B + bxl, by = ty0 / B + byl;
+        const size_t gb = (size_t)((uint32_t)(pair * p.nby + by) * (uint32_t)p.nbx + (uint32_t)bx);   // < 2^32 (launcher)
+        if (r_state == 1) sea_write<R>(p, gb, r_cost, r_pos, bx, by, out.nx, out.ny);
+        else out.worklist[atomicAdd(out.wl_count, 1u)] = (uint32_t)gb;
     }
 }
 
