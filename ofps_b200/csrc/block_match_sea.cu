@@ -301,14 +301,14 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
         if (bp != pos00) {
             const int d2 = (int)(bp >> 14);
             const int bdx = (int)(bp & 127u) - R, bdy = (int)((bp >> 7) & 127u) - R;
-            // rows that can hold a shorter vector: |dy| <= sqrt(d2) <= max + (min + 1) / 2 of (|dx|, |dy|) of the best
-            const int adx = abs(bdx), ady = abs(bdy);
-            const int r = min(R, max(adx, ady) + ((min(adx, ady) + 1) >> 1));
+            const int r = (int)sqrtf((float)d2);   // correctly rounded f32 sqrt of an integer < 2^13: floor is exact
             const int ya = max(-r, dy_lo), yb = min(r, dy_hi);
-            const uint32_t c00l = lane_in ? C00 : NONE;       // a window sum is < 2^16: idle lanes never match
+            // a window sum is < 2^16: idle lanes never match.  The best's own position always matches, so its column
+            // is left out of the row scan and tested on its own below.
+            const uint32_t c00l = lane_in && dx != bdx ? C00 : NONE;
             // G rows per vote: one load + one compare per candidate; the other three sub-sums, the position test and
             // the exact cost only where a first sub-sum matches.  Rows past yb are inside the plane (G - 1 <= N) and
-            // are masked below; the best's own position always matches and is masked too.
+            // are masked in the slow path.
             constexpr int G = N >= 8 ? 8 : 4;
             const uint16_t* qg = scol + (ya + R) * PW;
             for (int dyq = ya; dyq <= yb; dyq += G, qg += G * PW) {
@@ -321,7 +321,6 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
                 for (int j = 0; j < G; j++) code |= ((uint32_t)qg[j * PW] == c00l ? 1u : 0u) << j;
                 const int nrow = yb - dyq + 1;
                 if (nrow < G) code &= (1u << nrow) - 1u;
-                if (dx == bdx && bdy >= dyq && bdy < dyq + G) code &= ~(1u << (bdy - dyq));
                 unsigned rows = __reduce_or_sync(0xffffffffu, code);
                 while (rows) {
                     const int j = __ffs(rows) - 1;
@@ -338,6 +337,30 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
                         const uint32_t cp = __shfl_sync(0xffffffffu, pos, l);
                         if (cp >= bp) continue;
                         const uint32_t c = sea_exact<B, PW>(sP, wx0 + l - R, wy0 + dy, c0, c1, lane);
+                        evaluated++;
+                        if (c == 0) bp = cp;
+                    }
+                }
+            }
+            {   // the best's own column (its vector may have changed above: `bdx` is the column left out), lanes <-> dy
+                const uint16_t* col = sS + (byl * B + R) * PW + wx0 + bdx;
+#pragma unroll
+                for (int t = 0; t < (2 * R + 1 + 31) / 32; t++) {
+                    if (t > 0 && ya + 32 * t > yb) break;
+                    const int dy = ya + lane + 32 * t;
+                    const uint16_t* q = col + min(dy, yb) * PW;
+                    const uint32_t pos = sea_pos(bdx, dy, R);
+                    const bool hit = dy <= yb && dy != bdy && (uint32_t)q[0] == C00;
+                    if (__ballot_sync(0xffffffffu, hit) == 0u) continue;
+                    const bool zero = hit && pos < bp && (uint32_t)q[N] == C10 && (uint32_t)q[N * PW] == C01 &&
+                                      (uint32_t)q[N * PW + N] == C11;
+                    unsigned m = __ballot_sync(0xffffffffu, zero);
+                    while (m) {
+                        const int l = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t cp = __shfl_sync(0xffffffffu, pos, l);
+                        if (cp >= bp) continue;
+                        const uint32_t c = sea_exact<B, PW>(sP, wx0 + bdx, wy0 + ya + l + 32 * t, c0, c1, lane);
                         evaluated++;
                         if (c == 0) bp = cp;
                     }
