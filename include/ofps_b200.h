@@ -75,6 +75,10 @@ uint64_t ofpsb_launch_count(ofpsb_ctx *ctx);
  * out[0] = blocks seen, out[1] = blocks decided by the pruning pass, out[2] = exact SAD evaluations it
  * spent, out[3] = blocks sent to the exhaustive work list. */
 int ofpsb_block_match_stats(ofpsb_ctx *ctx, uint64_t out[4]);
+/* Device time of the kernels of the LAST default-path (fused SEA) block-match launch, from CUDA events recorded on the
+ * launching stream (needs option "block_match_profile" = 1; synchronises): out[0] = SEA kernel, out[1] = exhaustive
+ * work-list kernel, milliseconds. */
+int ofpsb_block_match_kernel_ms(ofpsb_ctx *ctx, float out[2]);
 /* The stream the context currently enqueues on (a cudaStream_t), for event timing by the caller. */
 void *ofpsb_get_stream(ofpsb_ctx *ctx);
 /* Tuning / test knobs; unknown keys return OFPSB_E_INVALID.
@@ -144,6 +148,48 @@ int ofpsb_block_match_strip_batch_dev(ofpsb_ctx *ctx, const uint8_t *d_prev, con
                                       int stride, size_t pair_stride, int n_pairs, int halo_top, int halo_bottom,
                                       int y_offset, int full_h, int block, int range, int metric,
                                       int16_t *d_mv_xy, uint32_t *d_cost, ofps_mv *d_entries);
+
+/* -------------------------------------------------------------- spatial tiling over the GPUs of one node
+ * One LARGE frame pair cut into horizontal strips of whole block rows, one rank (process or thread) per GPU
+ * (the multi-GPU form of the Decoder boundary, ofps/src/decoder.rs:45-73: `process_frame` of a
+ * tiled decoder calls ofpsb_tiled_upload / _publish / _match on its strip).  There is no exchange step: every rank
+ * exports its frame buffer once, maps its two neighbours' buffers, and the matching kernel reads the `range` halo
+ * rows of the previous frame straight from the neighbours' HBM over NVLink (tensor maps on peer-mapped memory).
+ *
+ *   create (same w, h, block, range, n_slots on every rank)  ->  export  ->  [exchange the 128-byte blobs]  ->
+ *   connect (IPC, other processes)  or  connect_local (ranks of ONE process)  ->  per frame: upload / write the slot,
+ *   publish  ->  match(prev_slot, cur_slot).
+ *
+ * Strips: block rows split evenly, the first (h/block) % world ranks take one more; the last rank also keeps the
+ * frame's remainder rows (h % block).  SAD only.  Outputs cover this rank's strip: nby*nbx blocks in raster order
+ * (strip order = raster order of the whole frame), entries normalised by the whole frame (av-decoder/src/lib.rs:404-419).
+ * Bit-identical to ofpsb_block_match on the whole frame. */
+typedef struct ofpsb_tiled ofpsb_tiled;
+#define OFPSB_TILED_HANDLE_BYTES 128
+int ofpsb_tiled_create(ofpsb_ctx *ctx, int rank, int world, int w, int h, int block, int range, int n_slots,
+                       ofpsb_tiled **out);
+void ofpsb_tiled_destroy(ofpsb_tiled *t);
+/* Geometry of this rank's strip: first pixel row, pixel rows matched (nby*block), rows stored (>= rows: the last
+ * rank keeps the remainder), blocks per row / block rows, byte stride of the device slots.  Any pointer may be NULL. */
+int ofpsb_tiled_info(ofpsb_tiled *t, int *y0, int *rows, int *own_rows, int *nbx, int *nby, int *stride);
+/* OFPSB_TILED_HANDLE_BYTES describing this rank's buffer for its neighbours (cudaIpcMemHandle + geometry). */
+int ofpsb_tiled_export(ofpsb_tiled *t, void *handle);
+/* Map the neighbours (blobs from THEIR ofpsb_tiled_export; NULL at the frame's top / bottom). */
+int ofpsb_tiled_connect(ofpsb_tiled *t, const void *up_handle, const void *down_handle);
+/* Same for ranks that live in this process (one thread per GPU, or several strips on one GPU in tests). */
+int ofpsb_tiled_connect_local(ofpsb_tiled *t, ofpsb_tiled *up, ofpsb_tiled *down);
+/* Device pointer to the first own row of frame slot `slot` (own_rows rows of `stride` bytes) — for producers that
+ * write the strip on the device.  ofpsb_tiled_upload copies own_rows rows from host memory (async on the context's
+ * stream). */
+void *ofpsb_tiled_slot_ptr(ofpsb_tiled *t, int slot);
+int ofpsb_tiled_upload(ofpsb_tiled *t, int slot, const uint8_t *host_rows, size_t host_stride);
+/* After the slot's rows are written (stream order): tell both neighbours (a 4-byte epoch in THEIR memory). */
+int ofpsb_tiled_publish(ofpsb_tiled *t, int slot);
+/* Match the strip of (prev_slot, cur_slot); device outputs (any may be NULL), asynchronous on the context's stream.
+ * wait_neighbours != 0: first wait (on the device) until both neighbours have published prev_slot as often as this
+ * rank has; 0: the caller has synchronised the ranks itself. */
+int ofpsb_tiled_match(ofpsb_tiled *t, int prev_slot, int cur_slot, ofps_mv *d_entries, int16_t *d_mv_xy, uint32_t *d_cost,
+                      int wait_neighbours);
 
 /* -------------------------------------------------------------- densifier
  * field_xy: gw*gh*2 floats, cell-major [x0,y0,x1,y1,...], cell = y*gw+x

@@ -41,6 +41,17 @@ SIGNATURES = {
     "ofpsb_launch_count": (C.c_uint64, [_vp]),
     "ofpsb_set_option": (C.c_int, [_vp, C.c_char_p, C.c_longlong]),
     "ofpsb_block_match_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "ofpsb_block_match_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "ofpsb_tiled_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "ofpsb_tiled_destroy": (None, [_vp]),
+    "ofpsb_tiled_info": (C.c_int, [_vp, _intp, _intp, _intp, _intp, _intp, _intp]),
+    "ofpsb_tiled_export": (C.c_int, [_vp, _vp]),
+    "ofpsb_tiled_connect": (C.c_int, [_vp, _vp, _vp]),
+    "ofpsb_tiled_connect_local": (C.c_int, [_vp, _vp, _vp]),
+    "ofpsb_tiled_slot_ptr": (_vp, [_vp, C.c_int]),
+    "ofpsb_tiled_upload": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t]),
+    "ofpsb_tiled_publish": (C.c_int, [_vp, C.c_int]),
+    "ofpsb_tiled_match": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
     "ofpsb_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "ofpsb_host_free": (None, [_vp]),
     "ofpsb_dev_alloc": (C.c_int, [_vp, C.POINTER(_vp), C.c_size_t]),
@@ -213,6 +224,11 @@ class Context:
         out = (C.c_uint64 * 4)()
         check(lib().ofpsb_block_match_stats(self._h, out))
         return {"blocks": out[0], "decided": out[1], "exact_evals": out[2], "worklist": out[3]}
+
+    def block_match_kernel_ms(self):
+        out = (C.c_float * 2)()
+        check(lib().ofpsb_block_match_kernel_ms(self._h, out))
+        return float(out[0]), float(out[1])
 
     def launch_count(self) -> int:
         return int(lib().ofpsb_launch_count(self._h))
@@ -467,3 +483,52 @@ def flo_write(path: str, field: np.ndarray):
     f = np.ascontiguousarray(field, np.float32)
     h, w = f.shape[:2]
     check(lib().ofpsb_flo_write(os.fsencode(path), f.ctypes.data, w, h))
+
+
+TILED_HANDLE_BYTES = 128
+
+
+class Tiled:
+    """One rank's strip of a spatially tiled frame (ofpsb_tiled_*, include/ofps_b200.h): halo rows of the previous frame
+    are read straight from the neighbours' HBM — no exchange step."""
+
+    def __init__(self, ctx: "Context", rank: int, world: int, w: int, h: int, block: int, search: int, n_slots: int = 2):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._t = _vp()
+        check(lib().ofpsb_tiled_create(ctx._h, rank, world, w, h, block, search, n_slots, C.byref(self._t)))
+        v = [C.c_int() for _ in range(6)]
+        check(lib().ofpsb_tiled_info(self._t, *[C.byref(x) for x in v]))
+        self.y0, self.rows, self.own_rows, self.nbx, self.nby, self.stride = (x.value for x in v)
+        self.n_blocks = self.nbx * self.nby
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(TILED_HANDLE_BYTES)
+        check(lib().ofpsb_tiled_export(self._t, buf))
+        return buf.raw
+
+    def connect(self, up: bytes | None, down: bytes | None):
+        check(lib().ofpsb_tiled_connect(self._t, up, down))
+
+    def connect_local(self, up: "Tiled | None", down: "Tiled | None"):
+        check(lib().ofpsb_tiled_connect_local(self._t, up._t if up else None, down._t if down else None))
+
+    def slot_ptr(self, slot: int) -> int:
+        return int(lib().ofpsb_tiled_slot_ptr(self._t, slot) or 0)
+
+    def upload(self, slot: int, own_rows: np.ndarray):
+        """own_rows: this rank's rows of the frame, u8 [own_rows, w] (C-contiguous rows)."""
+        a = np.ascontiguousarray(own_rows, np.uint8)
+        assert a.shape[0] == self.own_rows
+        check(lib().ofpsb_tiled_upload(self._t, slot, a.ctypes.data, a.strides[0]))
+        self.ctx.sync()          # `a` may be a temporary
+
+    def publish(self, slot: int):
+        check(lib().ofpsb_tiled_publish(self._t, slot))
+
+    def match(self, prev_slot: int, cur_slot: int, d_entries: int = 0, d_mv: int = 0, d_cost: int = 0, wait: bool = True):
+        check(lib().ofpsb_tiled_match(self._t, prev_slot, cur_slot, d_entries or None, d_mv or None, d_cost or None, int(wait)))
+
+    def close(self):
+        if self._t:
+            lib().ofpsb_tiled_destroy(self._t)
+            self._t = _vp()

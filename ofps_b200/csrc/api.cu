@@ -68,31 +68,6 @@ void PinBuf::release()
 
 namespace {
 
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DeviceGuard(int dev)
-    {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
-    }
-    ~DeviceGuard()
-    {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
-#define OFPSB_ENTER(ctx)                                           \
-    if (!(ctx)) {                                                  \
-        ::ofpsb::set_error("null context");                        \
-        return OFPSB_E_INVALID;                                    \
-    }                                                              \
-    ::ofpsb::DeviceGuard _guard((ctx)->device);                    \
-    if (!_guard.ok) {                                              \
-        ::ofpsb::set_error("cudaSetDevice(%d) failed", (ctx)->device); \
-        return OFPSB_E_CUDA;                                       \
-    }
-
 int get_event(ofpsb_ctx* ctx, size_t idx, cudaEvent_t* out)
 {
     while (ctx->events.size() <= idx) {
@@ -294,6 +269,8 @@ void ofpsb_destroy(ofpsb_ctx* ctx)
     for (DevBuf* b : bufs) b->release();
     ctx->h_misc.release();
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->bm_scratch.ev)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -356,6 +333,29 @@ int ofpsb_block_match_stats(ofpsb_ctx* ctx, uint64_t out[4])
     return OFPSB_OK;
 }
 
+int ofpsb_block_match_kernel_ms(ofpsb_ctx* ctx, float out[2])
+{
+    OFPSB_ENTER(ctx);
+    if (!out) {
+        set_error("block_match_kernel_ms: null output");
+        return OFPSB_E_INVALID;
+    }
+    out[0] = out[1] = 0.0f;
+    BlockMatchScratch& sc = ctx->bm_scratch;
+    if (!sc.profile || !sc.ev[0]) {
+        set_error("block_match_kernel_ms: option block_match_profile is off");
+        return OFPSB_E_INVALID;
+    }
+    OFPSB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (cudaEventElapsedTime(&out[0], sc.ev[0], sc.ev[1]) != cudaSuccess ||
+        cudaEventElapsedTime(&out[1], sc.ev[1], sc.ev[2]) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("block_match_kernel_ms: no default-path launch recorded yet");
+        return OFPSB_E_INVALID;
+    }
+    return OFPSB_OK;
+}
+
 int ofpsb_set_option(ofpsb_ctx* ctx, const char* key, long long value)
 {
     if (!ctx || !key) {
@@ -368,6 +368,12 @@ int ofpsb_set_option(ofpsb_ctx* ctx, const char* key, long long value)
     else if (!strcmp(key, "block_match_prune") && value >= 0 && value <= 1) ctx->opt_block_match_prune = (int)value;
     else if (!strcmp(key, "block_match_stats") && value >= 0 && value <= 1) ctx->bm_scratch.collect_stats = value != 0;
     else if (!strcmp(key, "block_match_prefetch_tiles") && value >= -1 && value <= 1000000) ctx->bm_scratch.prefetch_tiles = (int)value;
+    else if (!strcmp(key, "block_match_profile") && value >= 0 && value <= 1) {
+        OFPSB_ENTER(ctx);
+        for (int i = 0; i < 3 && value; i++)
+            if (!ctx->bm_scratch.ev[i]) OFPSB_CUDA_TRY(cudaEventCreate(&ctx->bm_scratch.ev[i]));
+        ctx->bm_scratch.profile = value != 0;
+    }
     else if (!strcmp(key, "block_match_pruner") && value >= 0 && value <= 1) ctx->bm_scratch.pruner = (int)value;
     else if (!strcmp(key, "block_match_chunk_pairs") && value >= 0 && value <= 32768) ctx->bm_scratch.chunk_pairs = (int)value;
     else {

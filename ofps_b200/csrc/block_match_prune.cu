@@ -460,9 +460,6 @@ static int pruned_chunk(const BlockMatchParams& p, BlockMatchScratch& sc, int sm
 // in chunks small enough to stay L2-resident ("block_match_chunk_pairs").  Measured on B200 (64 1080p pairs):
 // chunks of 4 / 8 / 16 / 32 / 64 pairs -> 20.1 / 17.1 / 15.7 / 14.6 / 14.3 us per pair: the path is bound by
 // instruction issue and TMA latency, not by HBM, and smaller launches only add tails — so the default is one chunk.
-int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int sm_count, cudaStream_t stream,
-                           uint64_t* launches);
-
 int launch_block_match_pruned(const BlockMatchParams& p, BlockMatchScratch& sc, int sm_count, cudaStream_t stream,
                               uint64_t* launches)
 {

@@ -208,6 +208,9 @@ struct SeaOut {
     unsigned long long* stats;   // [0] blocks, [1] resolved here, [2] exact evaluations, [3] blocks that ran the full scan
     float nx, ny;                // frame_norm = (1/W, 1/H), IEEE f32 divisions done once on the host
     int prefetch_tiles;          // L2 prefetch distance in tiles (0 = off): about the number of resident CTAs
+    // peer-halo mode (spatial tiling over GPUs): the previous-frame tensor holds this rank's own rows only; the halo
+    // rows above / below are read straight from the neighbours' HBM (tensor maps on peer-mapped memory)
+    int peer, own_rows, up_rows, has_up, has_down;
 };
 
 // current block -> registers: 8 (B=16) / 4 (B=8, lanes 0..15) bytes per lane, lane = 2 * row + half
@@ -510,7 +513,7 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
 #ifdef OFPSB_EMU
 struct SeaMaps { int unused; };
 #else
-struct SeaMaps { CUtensorMap prev, cur; };
+struct SeaMaps { CUtensorMap prev, cur, prev8, up8, down8; };   // *8: boxes of 8 rows (tiles at a strip seam)
 #endif
 
 template <int B, int R>
@@ -532,14 +535,28 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
     uint8_t* sC = sP + C::P_BYTES + C::S_BYTES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * SEA_TILE_W, ty0 = blockIdx.y * SEA_TILE_H, pair = blockIdx.z;
-    const int wx = tx0 - C::RA, wy = ty0 + p.halo_top - R;   // tensor row 0 of prev = first halo row
+    // tensor row 0 of prev = first halo row (halo rows stored with the strip) or first own row (peer-halo mode)
+    const int wx = tx0 - C::RA, wy = ty0 - R + (out.peer ? 0 : p.halo_top);
 #ifndef OFPSB_EMU
     if (tid == 0) {
         const uint32_t b32 = smem_u32(&bar);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b32));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(C::TX_BYTES) : "memory");
-        tma_load_3d(smem_u32(sP), &maps.prev, wx, wy, pair, b32);
+        if (out.peer && (wy < 0 || wy + C::PH > out.own_rows)) {
+            // a tile at a strip seam: 8 rows at a time, each group from the tensor that owns it — the neighbour's HBM
+            // over NVLink for the halo rows, zeros (out-of-tensor box) where the frame ends
+            static_assert(C::PH % 8 == 0 && (R % 8) == 0, "seam tiles are loaded in groups of 8 rows");
+            for (int g = 0; g < C::PH / 8; g++) {
+                const int y = wy + 8 * g;
+                const uint32_t dst = smem_u32(sP + g * 8 * C::PW);
+                if (y < 0 && out.has_up) tma_load_3d(dst, &maps.up8, wx, out.up_rows + y, pair, b32);
+                else if (y >= out.own_rows && out.has_down) tma_load_3d(dst, &maps.down8, wx, y - out.own_rows, pair, b32);
+                else tma_load_3d(dst, &maps.prev8, wx, y, pair, b32);
+            }
+        } else {
+            tma_load_3d(smem_u32(sP), &maps.prev, wx, wy, pair, b32);
+        }
         tma_load_3d(smem_u32(sC), &maps.cur, tx0, ty0, pair, b32);
         // the frames stream through the L2 once: pull the boxes of the tile a CTA that starts about one wave later will
         // load into the L2 now, so that its loads do not wait for HBM
@@ -549,7 +566,7 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
             const unsigned tz = t / per_pair, trem = t - tz * per_pair;
             if (tz < gridDim.z) {
                 const int py = (int)(trem / gridDim.x), px = (int)(trem - (unsigned)py * gridDim.x);
-                tma_prefetch_3d(&maps.prev, px * SEA_TILE_W - C::RA, py * SEA_TILE_H + p.halo_top - R, (int)tz);
+                tma_prefetch_3d(&maps.prev, px * SEA_TILE_W - C::RA, py * SEA_TILE_H - R + (out.peer ? 0 : p.halo_top), (int)tz);
                 tma_prefetch_3d(&maps.cur, px * SEA_TILE_W, py * SEA_TILE_H, (int)tz);
             }
         }
@@ -643,15 +660,26 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
 
 #ifndef OFPSB_EMU
 template <int B, int R>
-int launch_sea(const BlockMatchParams& p, const SeaOut& out, cudaStream_t stream)
+int launch_sea(const BlockMatchParams& p, const SeaOut& out, const SeaPeer* peer, cudaStream_t stream)
 {
     using C = SeaCfg<B, R>;
-    const int rows_prev = p.halo_top + p.strip_h + p.halo_bottom;
-    const uint8_t* prev_base = p.prev - (long long)p.halo_top * p.stride;
     SeaMaps maps;
-    if (!make_map(&maps.prev, prev_base, p.w, rows_prev, p.stride, p.pair_stride, p.n_pairs, C::PW, C::PH) ||
-        !make_map(&maps.cur, p.cur, p.w, p.strip_h, p.stride, p.pair_stride, p.n_pairs, C::CW, C::CH))
-        return 1;
+    if (peer) {
+        if (!make_map(&maps.prev, p.prev, p.w, peer->own_rows, p.stride, p.pair_stride, p.n_pairs, C::PW, C::PH) ||
+            !make_map(&maps.prev8, p.prev, p.w, peer->own_rows, p.stride, p.pair_stride, p.n_pairs, C::PW, 8))
+            return 1;
+        maps.up8 = maps.down8 = maps.prev8;
+        if (peer->up && !make_map(&maps.up8, peer->up, p.w, peer->up_rows, peer->up_stride, peer->up_pair_stride, p.n_pairs, C::PW, 8))
+            return 1;
+        if (peer->down && !make_map(&maps.down8, peer->down, p.w, peer->down_rows, peer->down_stride, peer->down_pair_stride, p.n_pairs, C::PW, 8))
+            return 1;
+    } else {
+        const int rows_prev = p.halo_top + p.strip_h + p.halo_bottom;
+        const uint8_t* prev_base = p.prev - (long long)p.halo_top * p.stride;
+        if (!make_map(&maps.prev, prev_base, p.w, rows_prev, p.stride, p.pair_stride, p.n_pairs, C::PW, C::PH)) return 1;
+        maps.prev8 = maps.up8 = maps.down8 = maps.prev;
+    }
+    if (!make_map(&maps.cur, p.cur, p.w, p.strip_h, p.stride, p.pair_stride, p.n_pairs, C::CW, C::CH)) return 1;
     static bool attr_set[64] = {};
     int dev = 0;
     OFPSB_CUDA_TRY(cudaGetDevice(&dev));
@@ -676,7 +704,7 @@ int launch_block_match_list(const BlockMatchParams& p, const uint32_t* d_list, c
 // Fused SEA search of one batch.  Returns 0 when launched, 1 when the path does not apply (metric, geometry,
 // alignment) — the caller then tries the other paths — and < 0 on error.
 int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int sm_count, cudaStream_t stream,
-                           uint64_t* launches)
+                           uint64_t* launches, const SeaPeer* peer, cudaEvent_t before_list)
 {
     if (p.metric != OFPSB_METRIC_SAD || !block_match_tma_usable(p)) return 1;
     const bool geom = (p.block == 16 || p.block == 8) && (p.range == 8 || p.range == 16);
@@ -685,6 +713,9 @@ int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int
     if (p.w < p.block || rows_prev < p.block) return 1;
     const long long total = (long long)p.nbx * p.nby * p.n_pairs;
     if (total >= 0xFFFFFFF0ll) return 1;
+    if (peer && ((reinterpret_cast<uintptr_t>(peer->up) | reinterpret_cast<uintptr_t>(peer->down) | (uintptr_t)peer->up_stride |
+                  (uintptr_t)peer->down_stride) & 15))
+        return 1;
     // scratch: [0] work-list count, [2..9] four 64-bit statistics, then the work list
     const size_t head = 16;
     if (int rc = sc.worklist.reserve((head + (size_t)total + 8) * sizeof(uint32_t))) return rc;
@@ -695,19 +726,31 @@ int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int
     out.nx = 1.0f / (float)p.w;          // av-decoder/src/lib.rs:404-405 (host code is built with -ffp-contract=off)
     out.ny = 1.0f / (float)p.full_h;
     out.prefetch_tiles = sc.prefetch_tiles >= 0 ? sc.prefetch_tiles : 3 * (sm_count > 0 ? sm_count : 148);
+    out.peer = peer ? 1 : 0;
+    out.own_rows = peer ? peer->own_rows : 0;
+    out.up_rows = peer ? peer->up_rows : 0;
+    out.has_up = peer && peer->up ? 1 : 0;
+    out.has_down = peer && peer->down ? 1 : 0;
+    if (peer) out.prefetch_tiles = 0;
     out.worklist = base + head;
     OFPSB_CUDA_TRY(cudaMemsetAsync(base, 0, head * sizeof(uint32_t), stream));
+    if (sc.profile && sc.ev[0]) OFPSB_CUDA_TRY(cudaEventRecord(sc.ev[0], stream));
     int rc = 1;
-    if (p.block == 16 && p.range == 16) rc = launch_sea<16, 16>(p, out, stream);
-    else if (p.block == 16 && p.range == 8) rc = launch_sea<16, 8>(p, out, stream);
-    else if (p.block == 8 && p.range == 16) rc = launch_sea<8, 16>(p, out, stream);
-    else if (p.block == 8 && p.range == 8) rc = launch_sea<8, 8>(p, out, stream);
+    if (p.block == 16 && p.range == 16) rc = launch_sea<16, 16>(p, out, peer, stream);
+    else if (p.block == 16 && p.range == 8) rc = launch_sea<16, 8>(p, out, peer, stream);
+    else if (p.block == 8 && p.range == 16) rc = launch_sea<8, 16>(p, out, peer, stream);
+    else if (p.block == 8 && p.range == 8) rc = launch_sea<8, 8>(p, out, peer, stream);
     if (rc) return rc;
+    if (sc.profile && sc.ev[1]) OFPSB_CUDA_TRY(cudaEventRecord(sc.ev[1], stream));
+    // the exhaustive kernel reads halo rows stored with the strip: in peer-halo mode they are copied on a side
+    // stream while the SEA kernel runs; `before_list` marks that copy
+    if (before_list) OFPSB_CUDA_TRY(cudaStreamWaitEvent(stream, before_list, 0));
     rc = launch_block_match_list(p, out.worklist, out.wl_count, sm_count, stream);
     if (rc != OFPSB_OK) {
         set_error("block_match: work-list kernel unavailable for block=%d range=%d", p.block, p.range);
         return rc < 0 ? rc : OFPSB_E_INVALID;
     }
+    if (sc.profile && sc.ev[2]) OFPSB_CUDA_TRY(cudaEventRecord(sc.ev[2], stream));
     if (launches) *launches += 2;
     return OFPSB_OK;
 }

@@ -78,11 +78,27 @@ int launch_block_match(const BlockMatchParams& p, cudaStream_t stream, uint64_t*
 struct BlockMatchScratch {
     DevBuf sums, worklist;
     bool collect_stats = false;
+    bool profile = false;     // record events around the SEA / work-list kernels (ofpsb_block_match_kernel_ms)
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     int prefetch_tiles = -1;  // SEA kernel: L2 prefetch distance in tiles (-1 = three CTAs per SM, 0 = off)
     int pruner = 0;           // 0 = fused SEA kernel where it applies (default), 1 = round-1 window-sum pipeline (tests / A-B)
     int chunk_pairs = 0;      // pairs per pruned chunk (0 = whole batch; smaller chunks stay L2-resident but measured slower)
     size_t l2_bytes = 0;
 };
+// Peer-halo mode of the SEA kernel (spatial tiling): p.prev = first OWN row, own_rows rows in this rank's memory; the
+// halo rows above / below come from the neighbours' tensors (null = frame border).
+struct SeaPeer {
+    int own_rows;
+    const uint8_t* up;      // first own row of the upper neighbour's strip (peer-mapped), up_rows rows
+    int up_rows, up_stride;
+    long long up_pair_stride;
+    const uint8_t* down;
+    int down_rows, down_stride;
+    long long down_pair_stride;
+};
+// Fused SEA kernel + exhaustive work list (block_match_sea.cu).  Returns 0 when launched, 1 when it does not apply.
+int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& scratch, int sm_count, cudaStream_t stream,
+                           uint64_t* launches, const SeaPeer* peer = nullptr, cudaEvent_t before_list = nullptr);
 // Exact pruned SAD search (window-sum bounds + exhaustive search of the undecided blocks only).
 // Returns 0 when launched, 1 when the path does not apply, < 0 on error.
 int launch_block_match_pruned(const BlockMatchParams& p, BlockMatchScratch& scratch, int sm_count, cudaStream_t stream,
@@ -177,3 +193,32 @@ struct ofpsb_ctx {
     ofpsb::DevBuf d_cv_src, d_cv_small, d_cv_gray, d_cv_rgba, d_cv_mask, d_cv_flow, d_cv_count;
     std::vector<cudaEvent_t> events;      // pool for the batch pipeline (no timing)
 };
+
+#ifndef OFPSB_EMU
+namespace ofpsb {
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define OFPSB_ENTER(ctx)                                           \
+    if (!(ctx)) {                                                  \
+        ::ofpsb::set_error("null context");                        \
+        return OFPSB_E_INVALID;                                    \
+    }                                                              \
+    ::ofpsb::DeviceGuard _guard((ctx)->device);                    \
+    if (!_guard.ok) {                                              \
+        ::ofpsb::set_error("cudaSetDevice(%d) failed", (ctx)->device); \
+        return OFPSB_E_CUDA;                                       \
+    }
+}  // namespace ofpsb
+#endif

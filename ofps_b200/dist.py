@@ -257,7 +257,10 @@ class TiledStreamMatcher:
         s, w = self.strip, self.w
         fb = self.rows * w
         prev = self.frames.data_ptr() + s.halo_top * w
-        self.ctx.block_match_strip_batch_dev(prev, prev + fb, w, s.rows, w, fb, self.n_frames - 1, s.halo_top, s.halo_bottom,
+        # rows below the last block row that this rank stores (the frame's remainder on the last rank) are valid
+        # search rows, exactly as in TiledBlockMatcher._launch and in the whole-frame rule
+        below = min(self.search, s.halo_bottom + s.own_rows - s.rows)
+        self.ctx.block_match_strip_batch_dev(prev, prev + fb, w, s.rows, w, fb, self.n_frames - 1, s.halo_top, below,
                                              s.y0, self.h, self.block, self.search, self.metric, None, None,
                                              self.entries.data_ptr())
 
@@ -269,3 +272,51 @@ class TiledStreamMatcher:
                 self.exchange()
             self.kernel_stream.wait_stream(self.comm_stream)
         self.match()
+
+
+class PeerTiledMatcher:
+    """Spatial tiling with NO exchange step (ofpsb_tiled_*, csrc/tiled.cu): every rank maps its neighbours' frame
+    buffers (CUDA IPC) and the matching kernel reads the halo rows of the previous frame straight from their HBM.
+    ``torch.distributed`` only carries the 128-byte handles once, at set-up; per pair there is no collective."""
+
+    def __init__(self, ctx, w: int, h: int, block: int, search: int, rank: int, world: int, n_slots: int = 2, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import capi
+        self.torch, self.ctx, self.rank, self.world, self.group = torch, ctx, rank, world, group
+        self.t = capi.Tiled(ctx, rank, world, w, h, block, search, n_slots)
+        self.w, self.h = w, h
+        if world > 1:
+            blobs = [None] * world
+            dist.all_gather_object(blobs, self.t.export(), group=group)
+            self.t.connect(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank + 1 < world else None)
+            dist.barrier(group=group)
+        dev = torch.device("cuda", ctx.device)
+        self.entries = torch.zeros((self.t.n_blocks, 4), dtype=torch.float32, device=dev)
+
+    def load(self, slot: int, frame: np.ndarray):
+        """This rank's rows of a whole host frame -> slot, then tell the neighbours."""
+        t = self.t
+        t.upload(slot, frame[t.y0:t.y0 + t.own_rows])
+        t.publish(slot)
+
+    def match(self, prev_slot: int = 0, cur_slot: int = 1, wait: bool = True):
+        self.t.match(prev_slot, cur_slot, self.entries.data_ptr(), wait=wait)
+
+    def gather_entries(self):
+        """All ranks' MotionEntry lists in strip (= raster) order, on every rank, as a numpy array."""
+        import torch.distributed as dist
+        torch = self.torch
+        self.ctx.sync()
+        if self.world == 1:
+            return self.entries.cpu().numpy()
+        counts = [None] * self.world
+        dist.all_gather_object(counts, self.t.n_blocks, group=self.group)
+        pad = torch.zeros((max(counts), 4), dtype=torch.float32, device=self.entries.device)
+        pad[:self.t.n_blocks] = self.entries
+        out = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(out, pad, group=self.group)
+        return np.concatenate([o[:n].cpu().numpy() for o, n in zip(out, counts)])
+
+    def close(self):
+        self.t.close()

@@ -34,7 +34,8 @@ def test_strips_equal_whole_frame(ctx, w, h, block, search, world):
     np.testing.assert_array_equal(np.concatenate(costs).reshape(whole["cost"].shape).astype(np.uint32), whole["cost"])
 
 
-@pytest.mark.parametrize("w,h,block,search,world", [(640, 368, 16, 16, 2), (512, 288, 8, 32, 3)])
+@pytest.mark.parametrize("w,h,block,search,world", [(640, 368, 16, 16, 2), (512, 288, 8, 32, 3), (640, 360, 16, 16, 2),
+                                                    (648, 364, 8, 16, 3)])
 def test_stream_strips_equal_whole_frames(ctx, w, h, block, search, world):
     frames = synth.make_stream(4, w, h, search)
     whole = ctx.block_match(frames[:-1], frames[1:], block, search, 0, want=("entries",))["entries"]
