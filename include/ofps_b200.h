@@ -190,6 +190,10 @@ int ofpsb_tiled_publish(ofpsb_tiled *t, int slot);
  * rank has; 0: the caller has synchronised the ranks itself. */
 int ofpsb_tiled_match(ofpsb_tiled *t, int prev_slot, int cur_slot, ofps_mv *d_entries, int16_t *d_mv_xy, uint32_t *d_cost,
                       int wait_neighbours);
+/* A stream of tiled frames in consecutive slots: pairs (first_slot + i, first_slot + i + 1), i < n_pairs, in ONE launch
+ * sequence (the per-launch latency of a strip is paid once per batch).  Outputs: n_pairs * nby*nbx, pair-major. */
+int ofpsb_tiled_match_stream(ofpsb_tiled *t, int first_slot, int n_pairs, ofps_mv *d_entries, int16_t *d_mv_xy,
+                             uint32_t *d_cost, int wait_neighbours);
 
 /* -------------------------------------------------------------- densifier
  * field_xy: gw*gh*2 floats, cell-major [x0,y0,x1,y1,...], cell = y*gw+x

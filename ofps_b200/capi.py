@@ -52,6 +52,7 @@ SIGNATURES = {
     "ofpsb_tiled_upload": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t]),
     "ofpsb_tiled_publish": (C.c_int, [_vp, C.c_int]),
     "ofpsb_tiled_match": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
+    "ofpsb_tiled_match_stream": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int]),
     "ofpsb_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "ofpsb_host_free": (None, [_vp]),
     "ofpsb_dev_alloc": (C.c_int, [_vp, C.POINTER(_vp), C.c_size_t]),
@@ -527,6 +528,10 @@ class Tiled:
 
     def match(self, prev_slot: int, cur_slot: int, d_entries: int = 0, d_mv: int = 0, d_cost: int = 0, wait: bool = True):
         check(lib().ofpsb_tiled_match(self._t, prev_slot, cur_slot, d_entries or None, d_mv or None, d_cost or None, int(wait)))
+
+    def match_stream(self, first_slot: int, n_pairs: int, d_entries: int = 0, d_mv: int = 0, d_cost: int = 0, wait: bool = True):
+        check(lib().ofpsb_tiled_match_stream(self._t, first_slot, n_pairs, d_entries or None, d_mv or None, d_cost or None,
+                                             int(wait)))
 
     def close(self):
         if self._t:

@@ -534,7 +534,10 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
     uint32_t* sS32 = reinterpret_cast<uint32_t*>(sP + C::P_BYTES);
     uint8_t* sC = sP + C::P_BYTES + C::S_BYTES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx0 = blockIdx.x * SEA_TILE_W, ty0 = blockIdx.y * SEA_TILE_H, pair = blockIdx.z;
+    // peer-halo mode: the tile rows at the two seams go first (last row, then row 0, 1, ...) so that their loads from
+    // the neighbours' memory overlap the rest of the strip instead of forming its tail
+    const int tile_row = out.peer ? (int)((blockIdx.y + gridDim.y - 1) % gridDim.y) : (int)blockIdx.y;
+    const int tx0 = blockIdx.x * SEA_TILE_W, ty0 = tile_row * SEA_TILE_H, pair = blockIdx.z;
     // tensor row 0 of prev = first halo row (halo rows stored with the strip) or first own row (peer-halo mode)
     const int wx = tx0 - C::RA, wy = ty0 - R + (out.peer ? 0 : p.halo_top);
 #ifndef OFPSB_EMU

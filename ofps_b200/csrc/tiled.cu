@@ -52,25 +52,47 @@ struct Neighbour {
 };
 
 struct GraphKey {
-    int prev, cur;
+    int prev, cur, n;
     void *entries, *mv, *cost;
-    bool operator==(const GraphKey& o) const { return prev == o.prev && cur == o.cur && entries == o.entries && mv == o.mv && cost == o.cost; }
+    bool wait;
+    bool operator==(const GraphKey& o) const
+    {
+        return prev == o.prev && cur == o.cur && n == o.n && entries == o.entries && mv == o.mv && cost == o.cost && wait == o.wait;
+    }
 };
 
-__global__ void tiled_publish_kernel(uint32_t* a, uint32_t* b, uint32_t v)
+// expected[slot] lives in this rank's own memory so that the wait kernel has constant arguments (graph capture)
+__global__ void tiled_publish_kernel(uint32_t* a, uint32_t* b, uint32_t* expected, uint32_t v)
 {
     __threadfence_system();   // the frame rows written before this kernel are visible before the flag
     if (a) *reinterpret_cast<volatile uint32_t*>(a) = v;
     if (b) *reinterpret_cast<volatile uint32_t*>(b) = v;
+    *expected = v;
     __threadfence_system();
 }
 
-__global__ void tiled_wait_kernel(const uint32_t* a, uint32_t va, const uint32_t* b, uint32_t vb)
+// a / b: flags of the first slot written by the upper / lower neighbour (two words per slot), n consecutive slots
+__global__ void tiled_wait_kernel(const uint32_t* a, const uint32_t* b, const uint32_t* expected, int n)
 {
     // epochs only grow; (int) difference so that a wrap after 2^31 publishes still compares correctly
-    while (a && (int)(*reinterpret_cast<const volatile uint32_t*>(a) - va) < 0) __nanosleep(200);
-    while (b && (int)(*reinterpret_cast<const volatile uint32_t*>(b) - vb) < 0) __nanosleep(200);
+    for (int i = 0; i < n; i++) {
+        const uint32_t v = expected[i];
+        while (a && (int)(*reinterpret_cast<const volatile uint32_t*>(a + 2 * i) - v) < 0) __nanosleep(100);
+        while (b && (int)(*reinterpret_cast<const volatile uint32_t*>(b + 2 * i) - v) < 0) __nanosleep(100);
+    }
     __threadfence_system();
+}
+
+// halo rows of the neighbours -> next to the strip (for the exhaustive work-list kernel): plain 16-byte loads from the
+// peer-mapped pointers (a kernel node costs less set-up than two 2-D copy-engine nodes for 2 x 123 KB).
+// blockIdx.y = slot; *_slot16: distance between consecutive slots in 16-byte units (own / upper / lower buffer)
+__global__ void tiled_halo_kernel(uint4* __restrict__ dst_up, const uint4* __restrict__ src_up, size_t n_up,
+                                  uint4* __restrict__ dst_dn, const uint4* __restrict__ src_dn, size_t n_dn, size_t own_slot16,
+                                  size_t up_slot16, size_t dn_slot16)
+{
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x, z = blockIdx.y;
+    for (size_t i = i0; i < n_up; i += step) dst_up[z * own_slot16 + i] = src_up[z * up_slot16 + i];
+    for (size_t i = i0; i < n_dn; i += step) dst_dn[z * own_slot16 + i] = src_dn[z * dn_slot16 + i];
 }
 
 }  // namespace
@@ -92,6 +114,7 @@ struct ofpsb_tiled {
 
     uint8_t* own(int slot) const { return buf + slot_bytes * (size_t)slot + (size_t)range * stride; }
     uint32_t* flags() const { return reinterpret_cast<uint32_t*>(buf + flags_off); }
+    uint32_t* expected() const { return flags() + 2 * n_slots; }   // this rank's own publish count per slot
 };
 
 namespace {
@@ -113,7 +136,9 @@ void plan_strip(int h, int block, int range, int rank, int world, ofpsb_tiled* t
     t->halo_bottom = range < below ? range : below;     // last rank: the frame's remainder rows (its own memory)
 }
 
-int enqueue_match(ofpsb_tiled* t, int prev_slot, int cur_slot, ofps_mv* d_entries, int16_t* d_mv, uint32_t* d_cost)
+// n_pairs > 1: pairs (prev_slot + i, prev_slot + i + 1) — consecutive slots of one stream — in ONE launch sequence
+int enqueue_match(ofpsb_tiled* t, int prev_slot, int cur_slot, int n_pairs, ofps_mv* d_entries, int16_t* d_mv, uint32_t* d_cost,
+                  bool wait_neighbours)
 {
     ofpsb_ctx* ctx = t->ctx;
     cudaStream_t S = ctx->stream;
@@ -123,8 +148,8 @@ int enqueue_match(ofpsb_tiled* t, int prev_slot, int cur_slot, ofps_mv* d_entrie
     p.w = t->w;
     p.strip_h = t->rows;
     p.stride = t->stride;
-    p.pair_stride = 0;
-    p.n_pairs = 1;
+    p.pair_stride = (long long)t->slot_bytes;
+    p.n_pairs = n_pairs;
     p.halo_top = t->halo_top;
     p.halo_bottom = t->halo_bottom;
     p.y_offset = t->y0;
@@ -140,16 +165,29 @@ int enqueue_match(ofpsb_tiled* t, int prev_slot, int cur_slot, ofps_mv* d_entrie
     if (p.nbx == 0 || p.nby == 0) return OFPSB_OK;
 
     const bool has_up = t->up.base && t->halo_top > 0, has_down = t->down.base && t->rank + 1 < t->world && t->halo_bottom > 0;
+    if (wait_neighbours && (has_up || has_down)) {
+        // lock-step protocol: every rank publishes a slot once per frame it puts there, so the neighbours' epoch of the
+        // slot must have reached this rank's own (kept on the device: constant kernel arguments, graph-capturable)
+        tiled_wait_kernel<<<1, 1, 0, S>>>(has_up ? t->flags() + 2 * prev_slot + 0 : nullptr,
+                                          has_down ? t->flags() + 2 * prev_slot + 1 : nullptr, t->expected() + prev_slot, n_pairs);
+        OFPSB_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+    }
     // halo rows next to the strip (for the exhaustive work-list kernel), copied from the neighbours on the side stream
     OFPSB_CUDA_TRY(cudaEventRecord(t->ev_fork, S));
     OFPSB_CUDA_TRY(cudaStreamWaitEvent(t->side, t->ev_fork, 0));
-    if (has_up)
-        OFPSB_CUDA_TRY(cudaMemcpy2DAsync(t->own(prev_slot) - (size_t)t->halo_top * t->stride, t->stride,
-                                         t->up.own(prev_slot) + (size_t)(t->up.own_rows - t->halo_top) * t->up.stride,
-                                         t->up.stride, t->w, t->halo_top, cudaMemcpyDeviceToDevice, t->side));
-    if (has_down)
-        OFPSB_CUDA_TRY(cudaMemcpy2DAsync(t->own(prev_slot) + (size_t)t->own_rows * t->stride, t->stride, t->down.own(prev_slot),
-                                         t->down.stride, t->w, t->halo_bottom, cudaMemcpyDeviceToDevice, t->side));
+    if (has_up || has_down) {
+        // strides are equal on every rank (same w): the halo rows are contiguous on both sides
+        const size_t n_up = has_up ? (size_t)t->halo_top * t->stride / 16 : 0, n_dn = has_down ? (size_t)t->halo_bottom * t->stride / 16 : 0;
+        tiled_halo_kernel<<<dim3(n_pairs > 8 ? 16 : 64, n_pairs), 256, 0, t->side>>>(
+            reinterpret_cast<uint4*>(t->own(prev_slot) - (size_t)t->halo_top * t->stride),
+            has_up ? reinterpret_cast<const uint4*>(t->up.own(prev_slot) + (size_t)(t->up.own_rows - t->halo_top) * t->up.stride) : nullptr,
+            n_up, reinterpret_cast<uint4*>(t->own(prev_slot) + (size_t)t->own_rows * t->stride),
+            has_down ? reinterpret_cast<const uint4*>(t->down.own(prev_slot)) : nullptr, n_dn, t->slot_bytes / 16,
+            has_up ? t->up.slot_bytes / 16 : 0, has_down ? t->down.slot_bytes / 16 : 0);
+        OFPSB_CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+    }
     OFPSB_CUDA_TRY(cudaEventRecord(t->ev_join, t->side));
 
     SeaPeer peer{};
@@ -158,13 +196,13 @@ int enqueue_match(ofpsb_tiled* t, int prev_slot, int cur_slot, ofps_mv* d_entrie
         peer.up = t->up.own(prev_slot);
         peer.up_rows = t->up.own_rows;
         peer.up_stride = t->up.stride;
-        peer.up_pair_stride = 0;
+        peer.up_pair_stride = (long long)t->up.slot_bytes;
     }
     if (has_down) {
         peer.down = t->down.own(prev_slot);
         peer.down_rows = t->down.own_rows;
         peer.down_stride = t->down.stride;
-        peer.down_pair_stride = 0;
+        peer.down_pair_stride = (long long)t->down.slot_bytes;
     }
     int rc = 1;
     if (ctx->opt_block_match_prune && ctx->opt_block_match_kernel == 0 && ctx->bm_scratch.pruner == 0)
@@ -202,7 +240,7 @@ int ofpsb_tiled_create(ofpsb_ctx* ctx, int rank, int world, int w, int h, int bl
     t->stride = (w + 15) & ~15;
     t->slot_bytes = (((size_t)t->stride * (size_t)(t->own_rows + 2 * range)) + 255) & ~(size_t)255;
     t->flags_off = t->slot_bytes * (size_t)n_slots;
-    t->alloc_bytes = t->flags_off + (((size_t)n_slots * 2 * sizeof(uint32_t) + 255) & ~(size_t)255);
+    t->alloc_bytes = t->flags_off + (((size_t)n_slots * 3 * sizeof(uint32_t) + 255) & ~(size_t)255);
     t->epoch.assign((size_t)n_slots, 0u);
     cudaError_t e = cudaMalloc(&t->buf, t->alloc_bytes);
     if (e == cudaSuccess) e = cudaMemset(t->buf, 0, t->alloc_bytes);
@@ -383,33 +421,20 @@ int ofpsb_tiled_publish(ofpsb_tiled* t, int slot)
     // I am the upper neighbour's DOWN side and the lower neighbour's UP side
     uint32_t* a = t->up.base ? t->up.flags() + 2 * slot + 1 : nullptr;
     uint32_t* b = t->down.base ? t->down.flags() + 2 * slot + 0 : nullptr;
-    if (a || b) {
-        tiled_publish_kernel<<<1, 1, 0, t->ctx->stream>>>(a, b, e);
+    {
+        tiled_publish_kernel<<<1, 1, 0, t->ctx->stream>>>(a, b, t->expected() + slot, e);
         OFPSB_CUDA_TRY(cudaGetLastError());
         t->ctx->launches++;
     }
     return OFPSB_OK;
 }
 
-int ofpsb_tiled_match(ofpsb_tiled* t, int prev_slot, int cur_slot, ofps_mv* d_entries, int16_t* d_mv_xy, uint32_t* d_cost,
-                      int wait_neighbours)
+static int tiled_match_impl(ofpsb_tiled* t, int prev_slot, int cur_slot, int n_pairs, ofps_mv* d_entries, int16_t* d_mv_xy,
+                            uint32_t* d_cost, int wait_neighbours)
 {
-    if (!t || prev_slot < 0 || prev_slot >= t->n_slots || cur_slot < 0 || cur_slot >= t->n_slots) {
-        set_error("tiled_match: invalid arguments");
-        return OFPSB_E_INVALID;
-    }
     OFPSB_ENTER(t->ctx);
     ofpsb_ctx* ctx = t->ctx;
-    if (wait_neighbours && (t->up.base || t->down.base)) {
-        // lock-step protocol: every rank publishes a slot once per frame it puts there, so the neighbours' epoch of the
-        // slot must have reached this rank's own
-        const uint32_t e = t->epoch[(size_t)prev_slot];
-        tiled_wait_kernel<<<1, 1, 0, ctx->stream>>>(t->up.base ? t->flags() + 2 * prev_slot + 0 : nullptr, e,
-                                                    t->down.base ? t->flags() + 2 * prev_slot + 1 : nullptr, e);
-        OFPSB_CUDA_TRY(cudaGetLastError());
-        ctx->launches++;
-    }
-    const GraphKey key{prev_slot, cur_slot, d_entries, d_mv_xy, d_cost};
+    const GraphKey key{prev_slot, cur_slot, n_pairs, d_entries, d_mv_xy, d_cost, wait_neighbours != 0};
     if (t->use_graph && !ctx->bm_scratch.collect_stats && !ctx->bm_scratch.profile) {
         for (auto& g : t->graphs)
             if (g.first == key) {
@@ -423,7 +448,7 @@ int ofpsb_tiled_match(ofpsb_tiled* t, int prev_slot, int cur_slot, ofps_mv* d_en
             cudaGraph_t graph = nullptr;
             OFPSB_CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             const uint64_t l0 = ctx->launches;
-            const int rc = enqueue_match(t, prev_slot, cur_slot, d_entries, d_mv_xy, d_cost);
+            const int rc = enqueue_match(t, prev_slot, cur_slot, n_pairs, d_entries, d_mv_xy, d_cost, wait_neighbours != 0);
             const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
             ctx->launches = l0;
             if (rc == OFPSB_OK && ce == cudaSuccess && graph) {
@@ -447,7 +472,28 @@ int ofpsb_tiled_match(ofpsb_tiled* t, int prev_slot, int cur_slot, ofps_mv* d_en
             t->seen.push_back(key);
         }
     }
-    return enqueue_match(t, prev_slot, cur_slot, d_entries, d_mv_xy, d_cost);
+    return enqueue_match(t, prev_slot, cur_slot, n_pairs, d_entries, d_mv_xy, d_cost, wait_neighbours != 0);
+}
+
+int ofpsb_tiled_match(ofpsb_tiled* t, int prev_slot, int cur_slot, ofps_mv* d_entries, int16_t* d_mv_xy, uint32_t* d_cost,
+                      int wait_neighbours)
+{
+    if (!t || prev_slot < 0 || prev_slot >= t->n_slots || cur_slot < 0 || cur_slot >= t->n_slots) {
+        set_error("tiled_match: invalid arguments");
+        return OFPSB_E_INVALID;
+    }
+    return tiled_match_impl(t, prev_slot, cur_slot, 1, d_entries, d_mv_xy, d_cost, wait_neighbours);
+}
+
+int ofpsb_tiled_match_stream(ofpsb_tiled* t, int first_slot, int n_pairs, ofps_mv* d_entries, int16_t* d_mv_xy, uint32_t* d_cost,
+                             int wait_neighbours)
+{
+    if (!t || n_pairs < 1 || first_slot < 0 || first_slot + n_pairs >= t->n_slots) {
+        set_error("tiled_match_stream: slots %d .. %d out of range (%d slots)", first_slot, first_slot + n_pairs,
+                  t ? t->n_slots : 0);
+        return OFPSB_E_INVALID;
+    }
+    return tiled_match_impl(t, first_slot, first_slot + 1, n_pairs, d_entries, d_mv_xy, d_cost, wait_neighbours);
 }
 
 }  // extern "C"

@@ -93,3 +93,33 @@ def test_tiled_argument_checks(ctx):
         assert t.y0 == 0 and t.rows == 176 and t.own_rows == 176 and (t.nbx, t.nby) == (40, 11)
     finally:
         t.close()
+
+
+def test_peer_tiled_stream_batch(ctx):
+    """ofpsb_tiled_match_stream: consecutive slots in one launch == pair by pair == whole frames."""
+    w, h, block, search, world, n = 640, 360, 16, 16, 3, 4
+    frames = synth.make_stream(n + 1, w, h, search, noise_lsb=1)
+    whole = ctx.block_match(frames[:-1], frames[1:], block, search, 0, want=("entries",))["entries"].reshape(n, -1, 4)
+    ts = [capi.Tiled(ctx, r, world, w, h, block, search, n + 1) for r in range(world)]
+    try:
+        for r, t in enumerate(ts):
+            t.connect_local(ts[r - 1] if r > 0 else None, ts[r + 1] if r + 1 < world else None)
+        for t in ts:
+            for s in range(n + 1):
+                t.upload(s, frames[s, t.y0:t.y0 + t.own_rows])
+                t.publish(s)
+        parts = []
+        for t in ts:
+            de = ctx.dev_alloc(n * t.n_blocks * 16)
+            for _ in range(3):
+                t.match_stream(0, n, de)
+            ctx.sync()
+            e = np.empty((n, t.n_blocks, 4), np.float32)
+            ctx.to_host(e, de)
+            ctx.dev_free(de)
+            parts.append(e)
+        got = np.concatenate(parts, axis=1)
+        assert got.tobytes() == whole.tobytes()
+    finally:
+        for t in ts:
+            t.close()
