@@ -149,6 +149,26 @@ int ofpsb_block_match_strip_batch_dev(ofpsb_ctx *ctx, const uint8_t *d_prev, con
                                       int y_offset, int full_h, int block, int range, int metric,
                                       int16_t *d_mv_xy, uint32_t *d_cost, ofps_mv *d_entries);
 
+/* -------------------------------------------------------------- streaming decoder
+ * The device side of `Decoder::process_frame` (ofps/src/decoder.rs:45-73) for a block-matching decoder: frames go in
+ * one at a time, the MotionEntry list of (previous frame, this frame) comes out.  Each frame is uploaded ONCE (the
+ * previous one is still in HBM); `frame` may be pageable memory (it is staged through a pinned ring by helper threads)
+ * or page-locked (handed to the copy engine as is: it must then stay unchanged until the pair it completes has been
+ * collected).  One caller thread at a time (the reference's plugins are Send,
+ * not Sync).  depth = frames in flight (>= 3; 4 or more lets submit run one frame ahead of collect). */
+typedef struct ofpsb_stream ofpsb_stream;
+int ofpsb_stream_open(ofpsb_ctx *ctx, int w, int h, int block, int range, int metric, int depth, ofpsb_stream **out);
+void ofpsb_stream_close(ofpsb_stream *s);
+/* Entries per pair: (w/block)*(h/block). */
+size_t ofpsb_stream_blocks(ofpsb_stream *s);
+/* Synchronous form: *n_entries = 0 for the first frame of the stream (`Ok(false)`: no motion vectors yet), else the
+ * entry count, `entries` filled (host memory, ofpsb_stream_blocks long). */
+int ofpsb_stream_push(ofpsb_stream *s, const uint8_t *frame, size_t stride, ofps_mv *entries, size_t *n_entries);
+/* Pipelined form: submit enqueues upload + kernels + read-back and returns; collect waits for the OLDEST outstanding
+ * pair (*n_entries = 0 when nothing is outstanding).  At most depth-2 pairs may be outstanding. */
+int ofpsb_stream_submit(ofpsb_stream *s, const uint8_t *frame, size_t stride);
+int ofpsb_stream_collect(ofpsb_stream *s, ofps_mv *entries, size_t *n_entries);
+
 /* -------------------------------------------------------------- spatial tiling over the GPUs of one node
  * One LARGE frame pair cut into horizontal strips of whole block rows, one rank (process or thread) per GPU
  * (the multi-GPU form of the Decoder boundary, ofps/src/decoder.rs:45-73: `process_frame` of a

@@ -215,8 +215,14 @@ public:
     template <typename F>
     BlockMatchDecoder(std::shared_ptr<Context> ctx, int width, int height, double framerate, F next_frame)
         : ctx_(std::move(ctx)), w_(width), h_(height), fps_(framerate), next_(std::move(next_frame)),
-          prev_((size_t)width * height), cur_((size_t)width * height)
+          cur_((size_t)width * height)
     {
+    }
+    BlockMatchDecoder(const BlockMatchDecoder&) = delete;
+    BlockMatchDecoder& operator=(const BlockMatchDecoder&) = delete;
+    ~BlockMatchDecoder()
+    {
+        if (stream_) ofpsb_stream_close(stream_);
     }
 
     PropList props_mut() { return {}; }
@@ -225,23 +231,28 @@ public:
 
     // Ok(true): vectors appended; Ok(false): frame had none (first frame); throws Error at end of stream /
     // on failure.  `out_frame` (RGBA, cleared then filled) and `skip_frames` as in decoder.rs:54-59.
+    // Every decoded frame goes through the streaming entry points (ofpsb_stream_*): it is uploaded once and the
+    // previous frame stays in HBM; a skipped frame is pushed too (it is the next pair's previous frame), its
+    // vectors are dropped.
     bool process_frame(MotionVectors& field, std::vector<RGBA>* out_frame, size_t* out_height, size_t skip_frames)
     {
+        if (!stream_ || s_block_ != block || s_range_ != range || s_metric_ != metric) {
+            if (stream_) ofpsb_stream_close(stream_);
+            stream_ = nullptr;
+            check(ofpsb_stream_open(ctx_->get(), w_, h_, block, range, metric, 4, &stream_));
+            s_block_ = block; s_range_ = range; s_metric_ = metric;
+            scratch_.resize(ofpsb_stream_blocks(stream_));
+        }
+        size_t nb = 0;
         for (size_t i = 0; i <= skip_frames; i++) {
-            prev_.swap(cur_);
             if (!next_(cur_.data())) throw Error(OFPSB_E_IO, "end of stream");
-            have_ = have_ < 2 ? have_ + 1 : 2;
+            check(ofpsb_stream_push(stream_, cur_.data(), (size_t)w_, scratch_.data(), &nb));
         }
         if (out_frame) {
             out_frame->clear();
             for (uint8_t v : cur_) out_frame->push_back({v, v, v, 255});
             if (out_height) *out_height = (size_t)h_;
         }
-        if (have_ < 2) return false;
-        size_t nb = 0;
-        scratch_.resize((size_t)(w_ / block) * (h_ / block));
-        check(ofpsb_block_match(ctx_->get(), prev_.data(), cur_.data(), w_, h_, w_, block, range, metric, nullptr, nullptr,
-                                scratch_.data(), &nb));
         size_t pushed = 0;
         for (size_t i = 0; i < nb; i++)
             if (emit_zero_motion || scratch_[i].mx != 0.0f || scratch_[i].my != 0.0f) {
@@ -256,9 +267,10 @@ private:
     int w_, h_;
     double fps_;
     std::function<bool(uint8_t*)> next_;
-    std::vector<uint8_t> prev_, cur_;
+    std::vector<uint8_t> cur_;
     MotionVectors scratch_;
-    int have_ = 0;
+    ofpsb_stream* stream_ = nullptr;
+    int s_block_ = 0, s_range_ = 0, s_metric_ = 0;
 };
 
 // ---- Frame source for BlockMatchDecoder: 8-bit luma from a raw file or a YUV4MPEG2 (.y4m) stream.

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libofps_b200.so")
-SOURCES = ["api.cu", "block_match.cu", "block_match_tma.cu", "block_match_prune.cu", "block_match_sea.cu", "tiled.cu", "densify.cu", "detect.cu", "almeida.cu", "cv_front.cu", "hole_fill.cu"]
+SOURCES = ["api.cu", "block_match.cu", "block_match_tma.cu", "block_match_prune.cu", "block_match_sea.cu", "tiled.cu", "stream.cu", "densify.cu", "detect.cu", "almeida.cu", "cv_front.cu", "hole_fill.cu"]
 HEADERS = [os.path.join(CSRC, h) for h in sorted(os.listdir(CSRC)) if h.endswith(".cuh")] + [os.path.join(HERE, "..", "include", "ofps_b200.h")]
 
 NVCC_FLAGS = [

@@ -42,6 +42,12 @@ SIGNATURES = {
     "ofpsb_set_option": (C.c_int, [_vp, C.c_char_p, C.c_longlong]),
     "ofpsb_block_match_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "ofpsb_block_match_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "ofpsb_stream_open": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "ofpsb_stream_close": (None, [_vp]),
+    "ofpsb_stream_blocks": (C.c_size_t, [_vp]),
+    "ofpsb_stream_push": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _szp]),
+    "ofpsb_stream_submit": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "ofpsb_stream_collect": (C.c_int, [_vp, _vp, _szp]),
     "ofpsb_tiled_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "ofpsb_tiled_destroy": (None, [_vp]),
     "ofpsb_tiled_info": (C.c_int, [_vp, _intp, _intp, _intp, _intp, _intp, _intp]),
@@ -537,3 +543,34 @@ class Tiled:
         if self._t:
             lib().ofpsb_tiled_destroy(self._t)
             self._t = _vp()
+
+
+class FrameStream:
+    """Streaming block-matching decoder (ofpsb_stream_*): frames in one at a time, MotionEntry lists out."""
+
+    def __init__(self, ctx: "Context", w: int, h: int, block: int, search: int, metric: int = 0, depth: int = 4):
+        self.ctx = ctx
+        self._s = _vp()
+        check(lib().ofpsb_stream_open(ctx._h, w, h, block, search, metric, depth, C.byref(self._s)))
+        self.n_blocks = int(lib().ofpsb_stream_blocks(self._s))
+
+    def push(self, frame: np.ndarray, out: np.ndarray | None = None):
+        """-> entries [n_blocks, 4] f32 of (previous frame, frame), or None for the first frame."""
+        out = np.empty((self.n_blocks, 4), np.float32) if out is None else out
+        n = C.c_size_t()
+        check(lib().ofpsb_stream_push(self._s, frame.ctypes.data, frame.strides[0], out.ctypes.data, C.byref(n)))
+        return out if n.value else None
+
+    def submit(self, frame: np.ndarray):
+        check(lib().ofpsb_stream_submit(self._s, frame.ctypes.data, frame.strides[0]))
+
+    def collect(self, out: np.ndarray | None = None):
+        out = np.empty((self.n_blocks, 4), np.float32) if out is None else out
+        n = C.c_size_t()
+        check(lib().ofpsb_stream_collect(self._s, out.ctypes.data, C.byref(n)))
+        return out if n.value else None
+
+    def close(self):
+        if self._s:
+            lib().ofpsb_stream_close(self._s)
+            self._s = _vp()

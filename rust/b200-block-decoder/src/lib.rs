@@ -17,11 +17,23 @@ pub struct BlockDecoder {
     fps: f64,
     block: usize,
     range: usize,
-    prev: Vec<u8>,
     cur: Vec<u8>,
-    have: usize,
     entries: Vec<sys::ofps_mv>,
+    /// streaming handle (ofpsb_stream_*): every frame is uploaded once, the previous one stays in HBM
+    stream: *mut sys::ofpsb_stream,
+    stream_geom: (usize, usize),
     ctx: sys::Context,
+}
+
+// the handle is used by one thread at a time (`&mut self`), like the reference's av-decoder (av-decoder/src/lib.rs:172)
+unsafe impl Send for BlockDecoder {}
+
+impl Drop for BlockDecoder {
+    fn drop(&mut self) {
+        if !self.stream.is_null() {
+            unsafe { sys::ofpsb_stream_close(self.stream) };
+        }
+    }
 }
 
 impl BlockDecoder {
@@ -38,10 +50,10 @@ impl BlockDecoder {
             fps: fps.parse()?,
             block: 16,
             range: 16,
-            prev: vec![0; width * height],
             cur: vec![0; width * height],
-            have: 0,
             entries: vec![],
+            stream: std::ptr::null_mut(),
+            stream_geom: (0, 0),
             ctx: sys::Context::new(0).map_err(|e| anyhow::anyhow!(e))?,
         })
     }
@@ -63,32 +75,40 @@ impl Decoder for BlockDecoder {
         out_frame: Option<(&mut Vec<RGBA>, &mut usize)>,
         skip_frames: usize,
     ) -> Result<bool> {
+        let block = self.block & !3; // the library takes multiples of 4
+        if self.stream.is_null() || self.stream_geom != (block, self.range) {
+            // properties are rewritten before every call (ofps-suite/src/app/detection.rs:131-141): reopen on change
+            if !self.stream.is_null() {
+                unsafe { sys::ofpsb_stream_close(self.stream) };
+                self.stream = std::ptr::null_mut();
+            }
+            let rc = unsafe {
+                sys::ofpsb_stream_open(
+                    self.ctx.0, self.width as i32, self.height as i32, block as i32, self.range as i32,
+                    sys::OFPSB_METRIC_SAD, 4, &mut self.stream,
+                )
+            };
+            if rc != sys::OFPSB_OK {
+                return Err(anyhow::anyhow!(sys::last_error()));
+            }
+            self.stream_geom = (block, self.range);
+            self.entries.resize(unsafe { sys::ofpsb_stream_blocks(self.stream) }, Default::default());
+        }
+        let mut n = 0usize;
         for _ in 0..=skip_frames {
-            std::mem::swap(&mut self.prev, &mut self.cur);
             self.reader.read_exact(&mut self.cur)?;
-            self.have = (self.have + 1).min(2);
+            // a skipped frame is pushed too: it is the next pair's previous frame; its vectors are overwritten
+            let rc = unsafe {
+                sys::ofpsb_stream_push(self.stream, self.cur.as_ptr(), self.width, self.entries.as_mut_ptr(), &mut n)
+            };
+            if rc != sys::OFPSB_OK {
+                return Err(anyhow::anyhow!(sys::last_error()));
+            }
         }
         if let Some((frame, height)) = out_frame {
             frame.clear();
             frame.extend(self.cur.iter().map(|&v| RGBA { r: v, g: v, b: v, a: 255 }));
             *height = self.height;
-        }
-        if self.have < 2 {
-            return Ok(false);
-        }
-        let block = self.block & !3; // the library takes multiples of 4
-        let nb = (self.width / block) * (self.height / block);
-        self.entries.resize(nb, Default::default());
-        let mut n = 0usize;
-        let rc = unsafe {
-            sys::ofpsb_block_match(
-                self.ctx.0, self.prev.as_ptr(), self.cur.as_ptr(), self.width as i32, self.height as i32,
-                self.width as i32, block as i32, self.range as i32, sys::OFPSB_METRIC_SAD, std::ptr::null_mut(),
-                std::ptr::null_mut(), self.entries.as_mut_ptr(), &mut n,
-            )
-        };
-        if rc != sys::OFPSB_OK {
-            return Err(anyhow::anyhow!(sys::last_error()));
         }
         field.extend(
             self.entries[..n].iter().map(|e| (na::Point2::new(e.px, e.py), na::Vector2::new(e.mx, e.my))),

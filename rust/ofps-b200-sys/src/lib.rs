@@ -16,6 +16,11 @@ pub struct ofpsb_ctx {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct ofpsb_stream {
+    _private: [u8; 0],
+}
+
 pub const OFPSB_OK: c_int = 0;
 pub const OFPSB_METRIC_SAD: c_int = 0;
 pub const OFPSB_METRIC_SSD: c_int = 1;
@@ -27,6 +32,15 @@ extern "C" {
     pub fn ofpsb_block_match(
         ctx: *mut ofpsb_ctx, prev: *const u8, cur: *const u8, w: c_int, h: c_int, stride: c_int, block: c_int,
         range: c_int, metric: c_int, mv_xy: *mut i16, cost: *mut u32, entries: *mut ofps_mv, n_blocks: *mut usize,
+    ) -> c_int;
+    pub fn ofpsb_stream_open(
+        ctx: *mut ofpsb_ctx, w: c_int, h: c_int, block: c_int, range: c_int, metric: c_int, depth: c_int,
+        out: *mut *mut ofpsb_stream,
+    ) -> c_int;
+    pub fn ofpsb_stream_close(s: *mut ofpsb_stream);
+    pub fn ofpsb_stream_blocks(s: *mut ofpsb_stream) -> usize;
+    pub fn ofpsb_stream_push(
+        s: *mut ofpsb_stream, frame: *const u8, stride: usize, entries: *mut ofps_mv, n_entries: *mut usize,
     ) -> c_int;
     pub fn ofpsb_block_dim(min_size: f32, subdivide: usize, dim: *mut usize) -> c_int;
     pub fn ofpsb_detect_block_motion(
