@@ -42,7 +42,7 @@ struct AlmeidaState {
     float rotation[4];   // running estimate (w,i,j,k)
     float a[9];          // normal matrix, accumulated at iteration 0
     unsigned int ticket;
-    unsigned int pad;
+    unsigned int epoch;   // persistent kernel: iterations finished (grid barrier between the 30 dependent iterations)
 };
 
 // ---- camera (f32, reference operation order; see oracle/camera_almeida.inc)
@@ -202,10 +202,14 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // ------------------------------------------------------------------ least-squares kernel
-// SINGLE: one CTA runs all 30 iterations (small inputs: RANSAC refits, the reference's <= 12,600
-// vector fields).  Otherwise one launch per iteration over a fixed grid; per-block f64 partials
-// are combined by the last block to arrive, in block order.
-template <bool SINGLE>
+// MODE 0 (SINGLE): one CTA runs all 30 iterations (small inputs: RANSAC refits).
+// MODE 2 (persistent): ONE launch of a co-resident grid runs all 30 iterations; per-block f64 partials are combined by
+//   the last block to arrive, in block order, and the other CTAs wait for its `epoch` store (a grid barrier costs
+//   ~2 us; 30 separate launches cost ~10 us each — the reference's own 12,600-vector fields took 0.35 ms of launches
+//   for ~30 us of arithmetic).
+// MODE 1: the same grid, one launch per iteration (fallback when a cooperative launch is not possible).
+constexpr int LSQ_SINGLE = 0, LSQ_STEPWISE = 1, LSQ_PERSISTENT = 2;
+template <int MODE>
 __global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __restrict__ entries,
                                                              const uint32_t* __restrict__ idx, size_t n_arg,
                                                              const uint32_t* __restrict__ n_ptr, const AlmeidaConst cst,
@@ -217,22 +221,23 @@ __global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __re
     __shared__ float s_rot[4];
     __shared__ float s_a[9];
     __shared__ bool s_last;
+    constexpr bool SINGLE = MODE == LSQ_SINGLE, PERSIST = MODE == LSQ_PERSISTENT;
     const int tid = threadIdx.x;
     const size_t n = n_ptr ? (size_t)*n_ptr : n_arg;
     const float4* e4 = reinterpret_cast<const float4*>(entries);
 
     if (n_ptr && n < 3) {   // solve_ypr_ransac: fewer than 3 inliers -> identity (almeida:246-250)
-        if (blockIdx.x == 0 && tid == 0 && (SINGLE || it_arg == LSQ_ITERS - 1)) {
+        if (blockIdx.x == 0 && tid == 0 && (SINGLE || PERSIST || it_arg == LSQ_ITERS - 1)) {
             out_quat[0] = 1.0f; out_quat[1] = 0.0f; out_quat[2] = 0.0f; out_quat[3] = 0.0f;
         }
         return;
     }
-    if (tid < 4) s_rot[tid] = SINGLE ? (tid == 0 ? 1.0f : 0.0f) : (it_arg == 0 ? (tid == 0 ? 1.0f : 0.0f) : state->rotation[tid]);
-    if (!SINGLE && it_arg > 0 && tid < 9) s_a[tid] = state->a[tid];
+    if (tid < 4) s_rot[tid] = (SINGLE || PERSIST || it_arg == 0) ? (tid == 0 ? 1.0f : 0.0f) : state->rotation[tid];
+    if (MODE == LSQ_STEPWISE && it_arg > 0 && tid < 9) s_a[tid] = state->a[tid];
     __syncthreads();
 
-    const int it_begin = SINGLE ? 0 : it_arg;
-    const int it_end = SINGLE ? LSQ_ITERS : it_arg + 1;
+    const int it_begin = MODE == LSQ_STEPWISE ? it_arg : 0;
+    const int it_end = MODE == LSQ_STEPWISE ? it_arg + 1 : LSQ_ITERS;
     for (int it = it_begin; it < it_end; it++) {
         float rot[4] = {s_rot[0], s_rot[1], s_rot[2], s_rot[3]};
         float rotm[9];
@@ -308,13 +313,32 @@ __global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __re
                     for (int k = 0; k < 4; k++) { state->rotation[k] = r4[k]; s_rot[k] = r4[k]; }
                     if (first) for (int k = 0; k < 9; k++) state->a[k] = a[k];
                     state->ticket = 0;
+                    if (PERSIST) {
+                        __threadfence();
+                        atomicExch(&state->epoch, (unsigned)(it + 1));
+                    }
+                }
+                __syncthreads();
+            }
+            if (PERSIST && it + 1 < it_end) {
+                // grid barrier: everybody needs the new rotation (and, after the first iteration, the normal matrix)
+                if (tid == 0 && !s_last) {
+                    while (*reinterpret_cast<volatile unsigned*>(&state->epoch) < (unsigned)(it + 1)) __nanosleep(64);
+                    __threadfence();
+                }
+                __syncthreads();
+                if (!s_last) {
+                    if (tid < 4) s_rot[tid] = __ldcg(&state->rotation[tid]);
+                    if (first && tid < 9) s_a[tid] = __ldcg(&state->a[tid]);
+                } else if (first && tid < 9) {
+                    s_a[tid] = __ldcg(&state->a[tid]);
                 }
                 __syncthreads();
             }
         }
     }
     // rotation.inverse() (almeida:199)
-    if ((SINGLE || (s_last && it_arg == LSQ_ITERS - 1)) && tid == 0) {
+    if ((SINGLE || (s_last && (PERSIST || it_arg == LSQ_ITERS - 1))) && tid == 0) {
         out_quat[0] = s_rot[0]; out_quat[1] = -s_rot[1]; out_quat[2] = -s_rot[2]; out_quat[3] = -s_rot[3];
     }
 }
@@ -533,7 +557,11 @@ void make_const(float aspect, float fov_y_deg, AlmeidaConst& c)
     c.fx = c.fy / aspect;
 }
 
-constexpr size_t SINGLE_MAX = 2048;    // entries handled by the one-CTA solver (above: one launch per iteration)
+// Entries handled by the one-CTA solver; above, a persistent multi-CTA grid with ONE entry per thread where the device
+// has room: every iteration is ~370 dependent warp instructions per entry, so the iteration time is set by the entries a
+// thread walks, not by the grid barrier (ncu r2: 12,600 entries at 4 per thread = 10 us per iteration; 2,000 entries in
+// one CTA = 7.5 us per iteration).
+constexpr size_t SINGLE_MAX = 512;
 
 int run_lsq(const ofps_mv* d_entries, const uint32_t* d_idx, size_t n, const uint32_t* d_n_ptr, const AlmeidaConst& cst,
             float* d_quat, AlmeidaScratch& s, int sm_count, cudaStream_t stream, uint64_t* launches)
@@ -541,19 +569,42 @@ int run_lsq(const ofps_mv* d_entries, const uint32_t* d_idx, size_t n, const uin
     if (int rc = s.state.reserve(sizeof(AlmeidaState))) return rc;
     AlmeidaState* st = s.state.as<AlmeidaState>();
     if (n <= SINGLE_MAX) {
-        almeida_lsq_kernel<true><<<1, LSQ_NT, 0, stream>>>(d_entries, d_idx, n, d_n_ptr, cst, st, nullptr, d_quat, 0);
+        almeida_lsq_kernel<LSQ_SINGLE><<<1, LSQ_NT, 0, stream>>>(d_entries, d_idx, n, d_n_ptr, cst, st, nullptr, d_quat, 0);
         OFPSB_CUDA_TRY(cudaGetLastError());
         if (launches) ++*launches;
         return OFPSB_OK;
     }
-    size_t want = (n + (size_t)LSQ_NT * 4 - 1) / ((size_t)LSQ_NT * 4);
-    const size_t cap = (size_t)(sm_count > 0 ? sm_count : 148) * 8;
+    // a co-resident grid: the device can hold `per_sm` CTAs per SM at once
+    static int per_sm_cached[64] = {};
+    int dev = 0;
+    OFPSB_CUDA_TRY(cudaGetDevice(&dev));
+    int per_sm = dev >= 0 && dev < 64 ? per_sm_cached[dev] : 0;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, almeida_lsq_kernel<LSQ_PERSISTENT>, LSQ_NT, 0) != cudaSuccess ||
+            per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 1;
+        }
+        if (dev >= 0 && dev < 64) per_sm_cached[dev] = per_sm;
+    }
+    const size_t want = (n + (size_t)LSQ_NT - 1) / (size_t)LSQ_NT;
+    const size_t cap = (size_t)(sm_count > 0 ? sm_count : 148) * (size_t)(per_sm < 4 ? per_sm : 4);
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     if (int rc = s.partial.reserve((size_t)grid * 12 * sizeof(double))) return rc;
     OFPSB_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(AlmeidaState), stream));
+    double* partial = s.partial.as<double>();
+    int it0 = 0;
+    void* args[] = {(void*)&d_entries, (void*)&d_idx, (void*)&n, (void*)&d_n_ptr, (void*)&cst, (void*)&st, (void*)&partial,
+                    (void*)&d_quat, (void*)&it0};
+    if (!s.no_cooperative &&
+        cudaLaunchCooperativeKernel((const void*)almeida_lsq_kernel<LSQ_PERSISTENT>, dim3(grid), dim3(LSQ_NT), args, 0, stream) ==
+            cudaSuccess) {
+        if (launches) ++*launches;
+        return OFPSB_OK;
+    }
+    cudaGetLastError();
     for (int it = 0; it < LSQ_ITERS; it++)
-        almeida_lsq_kernel<false><<<grid, LSQ_NT, 0, stream>>>(d_entries, d_idx, n, d_n_ptr, cst, st,
-                                                               s.partial.as<double>(), d_quat, it);
+        almeida_lsq_kernel<LSQ_STEPWISE><<<grid, LSQ_NT, 0, stream>>>(d_entries, d_idx, n, d_n_ptr, cst, st, partial, d_quat, it);
     OFPSB_CUDA_TRY(cudaGetLastError());
     if (launches) *launches += LSQ_ITERS;
     return OFPSB_OK;

@@ -179,7 +179,7 @@ int detect_from_device_entries(ofpsb_ctx* ctx, const ofps_mv* d_entries, size_t 
                                 &ctx->launches, ctx->opt_densify_path))
         return rc;
     if (int rc = launch_detect(ctx->d_field.as<float>(), dim, target_motion, min_size, d_island, d_res,
-                               ctx->d_detect_scratch, ctx->stream, &ctx->launches))
+                               ctx->d_detect_scratch, ctx->stream, &ctx->launches, ctx->opt_detect_union_find))
         return rc;
     OFPSB_CUDA_TRY(cudaMemcpyAsync(ctx->h_misc.ptr, d_res, field_xy ? rec + cells * 8 : rec, cudaMemcpyDeviceToHost,
                                    ctx->stream));
@@ -374,6 +374,8 @@ int ofpsb_set_option(ofpsb_ctx* ctx, const char* key, long long value)
             if (!ctx->bm_scratch.ev[i]) OFPSB_CUDA_TRY(cudaEventCreate(&ctx->bm_scratch.ev[i]));
         ctx->bm_scratch.profile = value != 0;
     }
+    else if (!strcmp(key, "detect_union_find") && value >= 0 && value <= 1) ctx->opt_detect_union_find = (int)value;
+    else if (!strcmp(key, "almeida_stepwise") && value >= 0 && value <= 1) ctx->almeida.no_cooperative = value != 0;
     else if (!strcmp(key, "block_match_pruner") && value >= 0 && value <= 1) ctx->bm_scratch.pruner = (int)value;
     else if (!strcmp(key, "block_match_chunk_pairs") && value >= 0 && value <= 32768) ctx->bm_scratch.chunk_pairs = (int)value;
     else {

@@ -133,7 +133,7 @@ struct DetectResult {   // written by the detector kernel (device), copied to ho
 // mean field (device, dim*dim*2) -> island field (device) + result record.
 int launch_detect(const float* d_mean_field, size_t dim, float target_motion, float min_size,
                   float* d_out_field, DetectResult* d_result, DevBuf& scratch, cudaStream_t stream,
-                  uint64_t* launches);
+                  uint64_t* launches, int force_union_find = 0);
 
 // MotionFieldDensifier::interpolate_empty_cells on the host (hole_fill.cu): sequential by definition.
 // sums / counts: 2*w*h floats each (the densifier state), updated in place.
@@ -142,6 +142,7 @@ void interpolate_empty_cells_host(float* sums, float* counts, size_t w, size_t h
 // ---------------------------------------------------------------------------- almeida
 struct AlmeidaScratch {
     DevBuf state, partial, hyp, inlier_idx, flags;
+    bool no_cooperative = false;   // tests: force the one-launch-per-iteration fallback of the multi-CTA solver
 };
 
 int launch_almeida(const ofps_mv* d_entries, size_t n, float aspect, float fov_y_deg, int use_ransac,
@@ -183,6 +184,7 @@ struct ofpsb_ctx {
     int opt_block_match_kernel = 0;
     int opt_batch_chunk_pairs = 0;
     int opt_block_match_prune = 1;
+    int opt_detect_union_find = 0;   // tests: force the union-find detector kernel on small grids
     ofpsb::BlockMatchScratch bm_scratch;
     // scratch
     ofpsb::DevBuf d_frames, d_mv, d_cost, d_entries, d_field, d_field2, d_counts, d_misc, d_detect_scratch;

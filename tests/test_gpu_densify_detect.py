@@ -153,3 +153,37 @@ def test_flow_field_bit_exact(ctx, oracle, w, h, n):
     assert got.tobytes() == want.tobytes()
     if n:
         assert np.isfinite(got).all() and (got != 0).any(axis=2).mean() > 0.99   # every hole is filled
+
+
+@pytest.mark.parametrize("dim_params", [(0.05, 3), (0.05, 7), (0.0625, 8), (1.0, 1), (0.25, 2), (0.01, 3)])
+def test_small_grid_detector_equals_union_find_and_oracle(ctx, oracle, dim_params):
+    """Grids up to 32 x 32 run the one-warp bit-mask kernel: random maps, serpentines (long geodesics), single cells,
+    full grids — against the oracle and against the union-find kernel forced on the same input."""
+    min_size, sub = dim_params
+    dim = ctx.detect_block_motion(np.zeros((0, 4), np.float32), min_size=min_size, subdivide=sub)[2]
+    assert dim <= 32
+    rng = np.random.default_rng(dim * 7 + sub)
+    cases = []
+    for fill in (0.15, 0.45, 0.6, 0.9):
+        m = rng.random((dim, dim)) < fill
+        cases.append([(x, y) for y in range(dim) for x in range(dim) if m[y, x]])
+    snake = []
+    for y in range(0, dim, 2):
+        snake += [(x, y) for x in range(dim)]
+        if y + 1 < dim:
+            snake.append((dim - 1 if (y // 2) % 2 == 0 else 0, y + 1))
+    cases += [snake, [(x, y) for y in range(dim) for x in range(dim)], [(dim // 2, dim // 2)], []]
+    for cells in cases:
+        if dim == 1:
+            e = np.array([(0.5, 0.5, 0.01, 0.0)] * len(cells), np.float32).reshape(-1, 4)
+        else:
+            # cell centres strictly inside (0, 1): nalgebra's all-components clamp collapses border coordinates
+            e = np.array([((x + 0.0) / (dim - 1) * 0.998 + 0.001, (y + 0.0) / (dim - 1) * 0.998 + 0.001, 0.01, 0.002) for x, y in cells],
+                         np.float32).reshape(-1, 4)
+        a = _detect_both(ctx, oracle, e, min_size=min_size, subdivide=sub)
+        ctx.set_option("detect_union_find", 1)
+        try:
+            b = ctx.detect_block_motion(e, min_size=min_size, subdivide=sub)
+        finally:
+            ctx.set_option("detect_union_find", 0)
+        assert a[:3] == tuple(b[:3]) and a[3].tobytes() == b[3].tobytes()
