@@ -97,3 +97,21 @@ def test_mfield_size_matches_reference_arithmetic():
         assert capi.mfield_size(*args) == tuple(pyref.mfield_size(*args)), args
     with pytest.raises(capi.OfpsError):
         capi.mfield_size(0, 10)
+
+
+def test_export_parity_vectors(tmp_path):
+    """tools/export_parity_vectors.py: the .mvec it writes is what the library's own reader (and the reference's
+    motion-loader) parses, and the expected outputs carry every frame."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "export_parity_vectors.py"), str(tmp_path)])
+    exp = json.load(open(tmp_path / "expected.json"))["frames"]
+    assert len(exp) >= 15
+    for i in (0, 3, len(exp) - 1):
+        e = capi.mvec_read(str(tmp_path / "inputs.mvec"), i)
+        assert len(e) == exp[i]["n_entries"]
+    two = next(f for f in exp if f.get("name", "").startswith("two equal islands"))
+    assert two["detector"]["has_motion"] and two["detector"]["area"] == 12
+    assert (tmp_path / "parity_check.rs").exists()
