@@ -54,7 +54,7 @@ NCU_TRAFFIC_BYTES_PRUNED_STEP = 904_700_000      # round-1 pipeline (kept for re
 # (profiles/r2_k1_sea_ncu.md) — below the algorithmic bytes because a frame is fetched once for its two pairs
 NCU_TRAFFIC_BYTES_SEA_STEP = 195_000_000
 NOISE_LSB = 2
-TILED_STREAM_PAIRS = 8
+TILED_STREAM_PAIRS = 16
 NCU_TRAFFIC_BYTES_EXHAUSTIVE_STEP = (PAIRS + 1) * W * H + PAIRS * NBLOCKS * 16
 
 
@@ -200,6 +200,8 @@ def run_ours(args):
     dev = f"cuda:{local_rank}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # "NCCL version ..." goes to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -299,6 +301,20 @@ def run_ours(args):
     e2e_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.result()
 
+    # ---- what the node can deliver: every rank copies its pinned stream to its GPU at the same time, nothing else running
+    # (the ceiling of `e2e` at this N: if per-rank e2e H2D rate sits on it, the host side is saturated, not the GPUs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        ctx.to_device(d_frames, host.array)
+    ctx.sync()
+    barrier()
+    h2d_ceiling = 4 * (PAIRS + 1) * frame_bytes / (time.perf_counter() - t0) / 1e9
+    if world > 1:
+        t = torch.tensor([h2d_ceiling], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        h2d_ceiling = float(t[0])
+
     # sanity: e2e results equal the device-resident ones (same frames) — not timed
     chk = np.empty((NBLOCKS, 4), np.float32)
     ctx.to_host(chk, d_entries + (PAIRS - 1) * NBLOCKS * 16)
@@ -373,7 +389,10 @@ def run_ours(args):
                                       "(bit-identical to exhaustive search; data-dependent)"},
             "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": PAIRS * NBLOCKS * 16, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_GBps_per_rank": h2d / (e2e_ms * 1e-3 / args.steps) / 1e9, "numa": numa,
+                    "h2d_GBps_per_rank": h2d / (e2e_ms * 1e-3 / args.steps) / 1e9,
+                    "h2d_ceiling_GBps_per_rank": h2d_ceiling, "numa": numa,
+                    "ceiling_note": "h2d_ceiling = all ranks copying the same pinned frames concurrently with no kernels "
+                                    "(min over ranks): e2e cannot exceed it",
                     "api": "ofpsb_block_match_batch (pinned host frames -> MotionEntry lists)"},
             "e2e_frame": {"value": W * H * n_pipe * world / t_pipe / 1e6, "unit": "Mpix/s", "frames_per_s_per_gpu": n_pipe / t_pipe,
                           "sync_push": {"value": W * H * n_sync * world / t_sync / 1e6, "us_per_frame": 1e6 * t_sync / n_sync},

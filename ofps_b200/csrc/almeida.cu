@@ -201,6 +201,21 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// Sum of the per-block partials of components k0..11 -> red[0][k].  16 lanes per component walk the blocks with stride
+// 16 in ascending order, then a 4-step xor tree: a fixed order (same bits in every CTA and in every launch mode), and a
+// few dozen dependent adds instead of gridDim.x.
+__device__ __forceinline__ void combine_partials(const double* __restrict__ buf, unsigned grid, int k0, double (*red)[12], int tid)
+{
+    const int k = tid >> 4, l = tid & 15;
+    if (k >= 12) return;                       // warps 6, 7 (LSQ_NT = 256): no component
+    double s = 0.0;
+    if (k >= k0)
+        for (unsigned b = (unsigned)l; b < grid; b += 16) s += __ldcg(&buf[(size_t)b * 12 + k]);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (l == 0 && k >= k0) red[0][k] = s;
+}
+
 // ------------------------------------------------------------------ least-squares kernel
 // MODE 0 (SINGLE): one CTA runs all 30 iterations (small inputs: RANSAC refits).
 // MODE 2 (persistent): ONE launch of a co-resident grid runs all 30 iterations; per-block f64 partials are combined by
@@ -283,6 +298,39 @@ __global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __re
                 for (int k = 0; k < 4; k++) s_rot[k] = r4[k];
             }
             __syncthreads();
+        } else if (PERSIST) {
+            // Every CTA publishes its partials, waits until all have (one monotonic counter, no reset), then combines ALL
+            // partials itself — in block order, so every CTA computes the same bits — and takes the solver step itself.
+            // One hop through L2 per iteration instead of three (ticket -> last block's result -> everybody reads it).
+            // Partials are double-buffered by iteration parity: a CTA can be one iteration ahead of a slow reader.
+            double* buf = partial + (size_t)(it & 1) * gridDim.x * 12;
+            if (tid < 12 && tid >= k0) {
+                double s = 0.0;
+                for (int w = 0; w < LSQ_NT / 32; w++) s += red[w][tid];
+                buf[(size_t)blockIdx.x * 12 + tid] = s;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                atomicAdd(&state->ticket, 1u);
+                const unsigned target = (unsigned)(it + 1) * gridDim.x;
+                while (*reinterpret_cast<volatile unsigned*>(&state->ticket) < target) __nanosleep(32);
+                __threadfence();
+            }
+            __syncthreads();
+            combine_partials(buf, gridDim.x, k0, red, tid);
+            __syncthreads();
+            if (tid == 0) {
+                float a[9], b[3];
+                for (int k = 0; k < 9; k++) a[k] = first ? (float)red[0][k] : s_a[k];
+                for (int k = 0; k < 3; k++) b[k] = (float)red[0][9 + k];
+                float r4[4] = {s_rot[0], s_rot[1], s_rot[2], s_rot[3]};
+                lsq_step(a, b, cst.eps_r, it, r4);
+                for (int k = 0; k < 4; k++) s_rot[k] = r4[k];
+                if (first) for (int k = 0; k < 9; k++) s_a[k] = a[k];
+            }
+            s_last = blockIdx.x == 0;
+            __syncthreads();
         } else {
             if (tid < 12 && tid >= k0) {
                 double s = 0.0;
@@ -298,11 +346,8 @@ __global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __re
             __syncthreads();
             if (s_last) {
                 __threadfence();
-                if (tid < 12 && tid >= k0) {
-                    double s = 0.0;
-                    for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(&partial[(size_t)b * 12 + tid]);
-                    red[0][tid] = s;
-                }
+                __syncthreads();   // red[][] of the block reduction has been consumed
+                combine_partials(partial, gridDim.x, k0, red, tid);
                 __syncthreads();
                 if (tid == 0) {
                     float a[9], b[3];
@@ -313,25 +358,6 @@ __global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __re
                     for (int k = 0; k < 4; k++) { state->rotation[k] = r4[k]; s_rot[k] = r4[k]; }
                     if (first) for (int k = 0; k < 9; k++) state->a[k] = a[k];
                     state->ticket = 0;
-                    if (PERSIST) {
-                        __threadfence();
-                        atomicExch(&state->epoch, (unsigned)(it + 1));
-                    }
-                }
-                __syncthreads();
-            }
-            if (PERSIST && it + 1 < it_end) {
-                // grid barrier: everybody needs the new rotation (and, after the first iteration, the normal matrix)
-                if (tid == 0 && !s_last) {
-                    while (*reinterpret_cast<volatile unsigned*>(&state->epoch) < (unsigned)(it + 1)) __nanosleep(64);
-                    __threadfence();
-                }
-                __syncthreads();
-                if (!s_last) {
-                    if (tid < 4) s_rot[tid] = __ldcg(&state->rotation[tid]);
-                    if (first && tid < 9) s_a[tid] = __ldcg(&state->a[tid]);
-                } else if (first && tid < 9) {
-                    s_a[tid] = __ldcg(&state->a[tid]);
                 }
                 __syncthreads();
             }
@@ -590,7 +616,7 @@ int run_lsq(const ofps_mv* d_entries, const uint32_t* d_idx, size_t n, const uin
     const size_t want = (n + (size_t)LSQ_NT - 1) / (size_t)LSQ_NT;
     const size_t cap = (size_t)(sm_count > 0 ? sm_count : 148) * (size_t)(per_sm < 4 ? per_sm : 4);
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    if (int rc = s.partial.reserve((size_t)grid * 12 * sizeof(double))) return rc;
+    if (int rc = s.partial.reserve((size_t)grid * 2 * 12 * sizeof(double))) return rc;
     OFPSB_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(AlmeidaState), stream));
     double* partial = s.partial.as<double>();
     int it0 = 0;
