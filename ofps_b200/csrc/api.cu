@@ -271,6 +271,8 @@ void ofpsb_destroy(ofpsb_ctx* ctx)
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->bm_scratch.ev)
         if (ev) cudaEventDestroy(ev);
+    if (ctx->bm_scratch.ev_listed) cudaEventDestroy(ctx->bm_scratch.ev_listed);
+    if (ctx->bm_scratch.h_listed) cudaFreeHost(ctx->bm_scratch.h_listed);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -367,6 +369,12 @@ int ofpsb_set_option(ofpsb_ctx* ctx, const char* key, long long value)
     else if (!strcmp(key, "batch_chunk_pairs") && value >= 0 && value <= 65535) ctx->opt_batch_chunk_pairs = (int)value;
     else if (!strcmp(key, "block_match_prune") && value >= 0 && value <= 1) ctx->opt_block_match_prune = (int)value;
     else if (!strcmp(key, "block_match_stats") && value >= 0 && value <= 1) ctx->bm_scratch.collect_stats = value != 0;
+    else if (!strcmp(key, "block_match_adaptive") && value >= 0 && value <= 1) {
+        ctx->bm_scratch.adaptive = (int)value;
+        ctx->bm_scratch.skip_calls = 0;
+        ctx->bm_scratch.listed_total = 0;
+    }
+    else if (!strcmp(key, "block_match_tile_h") && (value == 0 || value == 32 || value == 64)) ctx->bm_scratch.tile_h = (int)value;
     else if (!strcmp(key, "block_match_prefetch_tiles") && value >= -1 && value <= 1000000) ctx->bm_scratch.prefetch_tiles = (int)value;
     else if (!strcmp(key, "block_match_profile") && value >= 0 && value <= 1) {
         OFPSB_ENTER(ctx);

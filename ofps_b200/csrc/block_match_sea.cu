@@ -46,17 +46,17 @@ constexpr int SEA_WARPS = 8;
 constexpr int SEA_NT = SEA_WARPS * 32;
 constexpr int SEA_CAP = 32;                   // survivors a warp evaluates itself; more -> exhaustive work list
 constexpr uint32_t SEA_BIG = 0x00FFFFFFu;     // bound of an illegal candidate (real bounds are < 2^16)
-constexpr int SEA_TILE_W = 128, SEA_TILE_H = 64;
+constexpr int SEA_TILE_W = 128;   // tile height TH is a template parameter: 64 rows, or 32 for launches that do not fill the machine
 
-template <int B, int R>
+template <int B, int R, int TH>
 struct SeaCfg {
     static constexpr int N = B / 2;                       // sub-block edge
     static constexpr int ND = 2 * R + 1;
-    static constexpr int TBX = SEA_TILE_W / B, TBY = SEA_TILE_H / B;
+    static constexpr int TBX = SEA_TILE_W / B, TBY = TH / B;
     static constexpr int RA = (R + 15) & ~15;             // window origin on a 16-byte boundary (TMA, u8)
     static constexpr int PW = SEA_TILE_W + 2 * RA;        // previous-frame window: bytes per row
-    static constexpr int PH = SEA_TILE_H + 2 * R;
-    static constexpr int CW = SEA_TILE_W, CH = SEA_TILE_H;
+    static constexpr int PH = TH + 2 * R;
+    static constexpr int CW = SEA_TILE_W, CH = TH;
     static constexpr int WC = PW / 2;                     // window-sum plane: u32 (= two u16 sums) per row
     static constexpr int OR = PH - N + 1;                 // rows of window sums
     static constexpr int NSEG = SEA_NT / WC;              // row segments of the vertical pass
@@ -258,13 +258,13 @@ struct SeaResult {   // per-block result, kept by lane `it` of the warp until th
 // ---- step 3: one block, one warp ------------------------------------------------------------------------------------
 // sS: window sums (u16, pitch PW), sP: previous-frame window, sC: current tile.  (bxl, byl): block inside the tile.
 // pred: position code of the predictor.  Returns the winner (or, unresolved, the best found so far).
-template <int B, int R>
+template <int B, int R, int TH>
 __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, const uint8_t* __restrict__ sP,
                                                const uint8_t* __restrict__ sC, const uint32_t* __restrict__ s_csum,
                                                const BlockMatchParams& p, int bx, int by, int bxl, int byl, bool interior,
                                                uint32_t pred, int lane, uint32_t* __restrict__ s_list, const SeaOut& out)
 {
-    using C = SeaCfg<B, R>;
+    using C = SeaCfg<B, R, TH>;
     constexpr int N = C::N, ND = C::ND, PW = C::PW, CW = C::CW;
     constexpr uint32_t NONE = 0xFFFFFFFFu;
     const int x0 = bx * B, y0 = by * B;
@@ -516,11 +516,11 @@ struct SeaMaps { int unused; };
 struct SeaMaps { CUtensorMap prev, cur, prev8, up8, down8; };   // *8: boxes of 8 rows (tiles at a strip seam)
 #endif
 
-template <int B, int R>
+template <int B, int R, int TH>
 __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ SeaMaps maps, const BlockMatchParams p,
                                                         const SeaOut out)
 {
-    using C = SeaCfg<B, R>;
+    using C = SeaCfg<B, R, TH>;
     OFPSB_DYN_SMEM(smem);
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t s_list[SEA_WARPS][SEA_CAP];
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
     // peer-halo mode: the tile rows at the two seams go first (last row, then row 0, 1, ...) so that their loads from
     // the neighbours' memory overlap the rest of the strip instead of forming its tail
     const int tile_row = out.peer ? (int)((blockIdx.y + gridDim.y - 1) % gridDim.y) : (int)blockIdx.y;
-    const int tx0 = blockIdx.x * SEA_TILE_W, ty0 = tile_row * SEA_TILE_H, pair = blockIdx.z;
+    const int tx0 = blockIdx.x * SEA_TILE_W, ty0 = tile_row * TH, pair = blockIdx.z;
     // tensor row 0 of prev = first halo row (halo rows stored with the strip) or first own row (peer-halo mode)
     const int wx = tx0 - C::RA, wy = ty0 - R + (out.peer ? 0 : p.halo_top);
 #ifndef OFPSB_EMU
@@ -569,8 +569,8 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
             const unsigned tz = t / per_pair, trem = t - tz * per_pair;
             if (tz < gridDim.z) {
                 const int py = (int)(trem / gridDim.x), px = (int)(trem - (unsigned)py * gridDim.x);
-                tma_prefetch_3d(&maps.prev, px * SEA_TILE_W - C::RA, py * SEA_TILE_H - R + (out.peer ? 0 : p.halo_top), (int)tz);
-                tma_prefetch_3d(&maps.cur, px * SEA_TILE_W, py * SEA_TILE_H, (int)tz);
+                tma_prefetch_3d(&maps.prev, px * SEA_TILE_W - C::RA, py * TH - R + (out.peer ? 0 : p.halo_top), (int)tz);
+                tma_prefetch_3d(&maps.cur, px * SEA_TILE_W, py * TH, (int)tz);
             }
         }
     }
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
 
     // the whole tile is interior when no candidate of any of its blocks leaves the frame (CTA-uniform)
     const bool interior = tx0 - R >= 0 && tx0 + SEA_TILE_W + R <= p.w && ty0 - R >= -p.halo_top &&
-                          ty0 + SEA_TILE_H + R <= p.strip_h + p.halo_bottom &&
+                          ty0 + TH + R <= p.strip_h + p.halo_bottom &&
                           tx0 / B + C::TBX <= p.nbx && ty0 / B + C::TBY <= p.nby;
     const uint16_t* sS = reinterpret_cast<const uint16_t*>(sS32);
 
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
         const int byl = it / C::CPW, bxl = warp * C::CPW + it % C::CPW;
         const int bx = tx0 / B + bxl, by = ty0 / B + byl;
         if (bx >= p.nbx || by >= p.nby) continue;
-        const SeaResult res = sea_block<B, R>(sS, sP, sC, s_csum, p, bx, by, bxl, byl, interior, pred, lane, s_list[warp], out);
+        const SeaResult res = sea_block<B, R, TH>(sS, sP, sC, s_csum, p, bx, by, bxl, byl, interior, pred, lane, s_list[warp], out);
         pred = res.pos;
         if (lane == it) {
             r_cost = res.cost;
@@ -662,10 +662,10 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
 }
 
 #ifndef OFPSB_EMU
-template <int B, int R>
-int launch_sea(const BlockMatchParams& p, const SeaOut& out, const SeaPeer* peer, cudaStream_t stream)
+template <int B, int R, int TH>
+int launch_sea_th(const BlockMatchParams& p, const SeaOut& out, const SeaPeer* peer, cudaStream_t stream)
 {
-    using C = SeaCfg<B, R>;
+    using C = SeaCfg<B, R, TH>;
     SeaMaps maps;
     if (peer) {
         if (!make_map(&maps.prev, p.prev, p.w, peer->own_rows, p.stride, p.pair_stride, p.n_pairs, C::PW, C::PH) ||
@@ -687,13 +687,22 @@ int launch_sea(const BlockMatchParams& p, const SeaOut& out, const SeaPeer* peer
     int dev = 0;
     OFPSB_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        OFPSB_CUDA_TRY(cudaFuncSetAttribute(sea_kernel<B, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        OFPSB_CUDA_TRY(cudaFuncSetAttribute(sea_kernel<B, R, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    const dim3 grid((p.nbx * B + SEA_TILE_W - 1) / SEA_TILE_W, (p.nby * B + SEA_TILE_H - 1) / SEA_TILE_H, p.n_pairs);
-    sea_kernel<B, R><<<grid, SEA_NT, C::SMEM_BYTES, stream>>>(maps, p, out);
+    const dim3 grid((p.nbx * B + SEA_TILE_W - 1) / SEA_TILE_W, (p.nby * B + TH - 1) / TH, p.n_pairs);
+    sea_kernel<B, R, TH><<<grid, SEA_NT, C::SMEM_BYTES, stream>>>(maps, p, out);
     OFPSB_CUDA_TRY(cudaGetLastError());
     return OFPSB_OK;
+}
+// 64-row tiles amortise the window sums best; a launch of fewer tiles than about two waves of resident CTAs (a single
+// 1080p pair, a strip of a tiled frame) is bound by the latency of one CTA instead: half-height tiles halve it.
+template <int B, int R>
+int launch_sea(const BlockMatchParams& p, const SeaOut& out, const SeaPeer* peer, cudaStream_t stream, int sm_count, int tile_h)
+{
+    const long long tiles64 = (long long)((p.nbx * B + SEA_TILE_W - 1) / SEA_TILE_W) * ((p.nby * B + 63) / 64) * p.n_pairs;
+    const bool small = tile_h == 32 || (tile_h == 0 && tiles64 <= 6ll * (sm_count > 0 ? sm_count : 148));
+    return small ? launch_sea_th<B, R, 32>(p, out, peer, stream) : launch_sea_th<B, R, 64>(p, out, peer, stream);
 }
 #endif
 
@@ -719,6 +728,18 @@ int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int
     if (peer && ((reinterpret_cast<uintptr_t>(peer->up) | reinterpret_cast<uintptr_t>(peer->down) | (uintptr_t)peer->up_stride |
                   (uintptr_t)peer->down_stride) & 15))
         return 1;
+    // content feedback from the previous SEA launch (never blocks: an unfinished read-back is simply not used yet)
+    if (sc.adaptive && !peer && !sc.collect_stats) {
+        if (sc.ev_listed && sc.listed_total > 0 && cudaEventQuery(sc.ev_listed) == cudaSuccess) {
+            if ((double)sc.h_listed[0] > 0.6 * (double)sc.listed_total) sc.skip_calls = 15;
+            sc.listed_total = 0;
+        }
+        cudaGetLastError();
+        if (sc.skip_calls > 0) {
+            sc.skip_calls--;
+            return 1;   // the caller runs the exhaustive kernels
+        }
+    }
     // scratch: [0] work-list count, [2..9] four 64-bit statistics, then the work list
     const size_t head = 16;
     if (int rc = sc.worklist.reserve((head + (size_t)total + 8) * sizeof(uint32_t))) return rc;
@@ -739,10 +760,10 @@ int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int
     OFPSB_CUDA_TRY(cudaMemsetAsync(base, 0, head * sizeof(uint32_t), stream));
     if (sc.profile && sc.ev[0]) OFPSB_CUDA_TRY(cudaEventRecord(sc.ev[0], stream));
     int rc = 1;
-    if (p.block == 16 && p.range == 16) rc = launch_sea<16, 16>(p, out, peer, stream);
-    else if (p.block == 16 && p.range == 8) rc = launch_sea<16, 8>(p, out, peer, stream);
-    else if (p.block == 8 && p.range == 16) rc = launch_sea<8, 16>(p, out, peer, stream);
-    else if (p.block == 8 && p.range == 8) rc = launch_sea<8, 8>(p, out, peer, stream);
+    if (p.block == 16 && p.range == 16) rc = launch_sea<16, 16>(p, out, peer, stream, sm_count, sc.tile_h);
+    else if (p.block == 16 && p.range == 8) rc = launch_sea<16, 8>(p, out, peer, stream, sm_count, sc.tile_h);
+    else if (p.block == 8 && p.range == 16) rc = launch_sea<8, 16>(p, out, peer, stream, sm_count, sc.tile_h);
+    else if (p.block == 8 && p.range == 8) rc = launch_sea<8, 8>(p, out, peer, stream, sm_count, sc.tile_h);
     if (rc) return rc;
     if (sc.profile && sc.ev[1]) OFPSB_CUDA_TRY(cudaEventRecord(sc.ev[1], stream));
     // the exhaustive kernel reads halo rows stored with the strip: in peer-halo mode they are copied on a side
@@ -754,6 +775,24 @@ int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int
         return rc < 0 ? rc : OFPSB_E_INVALID;
     }
     if (sc.profile && sc.ev[2]) OFPSB_CUDA_TRY(cudaEventRecord(sc.ev[2], stream));
+    if (sc.adaptive && !peer && !sc.collect_stats) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cap);
+        if (cap == cudaStreamCaptureStatusNone) {
+            if (!sc.h_listed) {
+                if (cudaHostAlloc(reinterpret_cast<void**>(&sc.h_listed), 64, cudaHostAllocDefault) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&sc.ev_listed, cudaEventDisableTiming) != cudaSuccess) {
+                    cudaGetLastError();
+                    sc.adaptive = 0;
+                }
+            }
+            if (sc.adaptive) {
+                OFPSB_CUDA_TRY(cudaMemcpyAsync(sc.h_listed, out.wl_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+                OFPSB_CUDA_TRY(cudaEventRecord(sc.ev_listed, stream));
+                sc.listed_total = total;
+            }
+        }
+    }
     if (launches) *launches += 2;
     return OFPSB_OK;
 }

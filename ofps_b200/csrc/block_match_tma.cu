@@ -424,15 +424,20 @@ int launch_list(const BlockMatchParams& p, const uint32_t* d_list, const uint32_
     long long tiles = (total + TBX - 1) / TBX;
     const long long cap = (long long)(sm_count > 0 ? sm_count : 148) * 8;
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+    static bool attr_set[2][64] = {};   // per (metric, device): the attribute call costs as much as a launch
+    int dev = 0;
+    OFPSB_CUDA_TRY(cudaGetDevice(&dev));
+    const bool need_attr = dev < 0 || dev >= 64 || !attr_set[p.metric == OFPSB_METRIC_SAD ? 0 : 1][dev];
     if (p.metric == OFPSB_METRIC_SAD) {
         auto k = block_match_list_kernel<B, R, G, TBX, NT, OFPSB_METRIC_SAD>;
-        OFPSB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        if (need_attr) OFPSB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         k<<<grid, NT, C::SMEM_BYTES, stream>>>(mp, mc, p, d_list, d_count);
     } else {
         auto k = block_match_list_kernel<B, R, G, TBX, NT, OFPSB_METRIC_SSD>;
-        OFPSB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        if (need_attr) OFPSB_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         k<<<grid, NT, C::SMEM_BYTES, stream>>>(mp, mc, p, d_list, d_count);
     }
+    if (dev >= 0 && dev < 64) attr_set[p.metric == OFPSB_METRIC_SAD ? 0 : 1][dev] = true;
     OFPSB_CUDA_TRY(cudaGetLastError());
     return OFPSB_OK;
 }
@@ -452,6 +457,10 @@ int launch_block_match_list(const BlockMatchParams& p, const uint32_t* d_list, c
                             cudaStream_t stream)
 {
     if (!block_match_tma_usable(p)) return 1;
+    // a launch of a few thousand blocks lists a few hundred at most: one block per tile and short dy groups keep the
+    // latency of the (single) wave low — the search of a listed block is spread over 198 threads instead of 66
+    if (p.block == 16 && p.range == 16 && (long long)p.nbx * p.nby * p.n_pairs <= 40000)
+        return launch_list<16, 16, 6, 1, 224>(p, d_list, d_count, sm_count, stream);
     if (p.block == 16 && p.range == 16) return launch_list<16, 16, 17, 4, 288>(p, d_list, d_count, sm_count, stream);
     if (p.block == 16 && p.range == 8) return launch_list<16, 8, 17, 4, 96>(p, d_list, d_count, sm_count, stream);
     if (p.block == 16 && p.range == 32) return launch_list<16, 32, 13, 2, 672>(p, d_list, d_count, sm_count, stream);

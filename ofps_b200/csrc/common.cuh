@@ -80,6 +80,15 @@ struct BlockMatchScratch {
     bool collect_stats = false;
     bool profile = false;     // record events around the SEA / work-list kernels (ofpsb_block_match_kernel_ms)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // content feedback: the work-list count of every SEA launch is read back asynchronously; when most blocks of the last
+    // launch ended on the work list (heavy noise: the bounds prune nothing) the next launches go straight to the exhaustive
+    // kernel, with a SEA launch every 16th call to notice when the content changes.  Results are identical either way.
+    uint32_t* h_listed = nullptr;       // pinned: [0] listed blocks of the last SEA launch
+    cudaEvent_t ev_listed = nullptr;
+    long long listed_total = 0;         // blocks of that launch
+    int skip_calls = 0;                 // SEA launches still to skip
+    int adaptive = 1;
+    int tile_h = 0;           // SEA kernel tile height: 0 = by launch size, 32 / 64 = forced (tests, A-B)
     int prefetch_tiles = -1;  // SEA kernel: L2 prefetch distance in tiles (-1 = three CTAs per SM, 0 = off)
     int pruner = 0;           // 0 = fused SEA kernel where it applies (default), 1 = round-1 window-sum pipeline (tests / A-B)
     int chunk_pairs = 0;      // pairs per pruned chunk (0 = whole batch; smaller chunks stay L2-resident but measured slower)

@@ -33,7 +33,7 @@ def emu():
     return L
 
 
-def run_sea(L, prev, cur, block, search, hint=1, strip=None):
+def run_sea(L, prev, cur, block, search, tile_h=64, strip=None):
     """prev/cur: [h, w] or [n, h, w] u8.  strip = (y0, rows): match only cur rows y0 .. y0+rows with the halo rows
     of prev that exist in the frame.  Returns mv, cost, entries, resolved mask, stats."""
     if prev.ndim == 2:
@@ -51,7 +51,7 @@ def run_sea(L, prev, cur, block, search, hint=1, strip=None):
     stats = np.zeros(4, np.uint64)
     rc = L.emu_block_match_sea(prev.ctypes.data + y0 * w, cur.ctypes.data + y0 * w, w, rows, w, h * w, n, top, bot, y0, h,
                                block, search, mv.ctypes.data, cost.ctypes.data, ent.ctypes.data, wl.ctypes.data,
-                               cnt.ctypes.data, stats.ctypes.data, hint)
+                               cnt.ctypes.data, stats.ctypes.data, tile_h)
     assert rc == 0
     resolved = np.ones(n * nby * nbx, bool)
     resolved[wl[:cnt[0]]] = False
@@ -86,10 +86,17 @@ def test_sea_matches_oracle(emu, oracle, block, search, w, h, noise):
           f"full scans {stats[3] / stats[0]:.2f}")
 
 
-@pytest.mark.parametrize("hint", [0, 1])
-def test_sea_stream_batch(emu, oracle, hint):
+@pytest.mark.parametrize("tile_h", [64, 32])
+def test_sea_stream_batch(emu, oracle, tile_h):
     fr = synth.make_stream(3, 384, 208, 16)
-    check(emu, oracle, fr[:-1], fr[1:], 16, 16, min_resolved=0.6, hint=hint)
+    check(emu, oracle, fr[:-1], fr[1:], 16, 16, min_resolved=0.6, tile_h=tile_h)
+
+
+@pytest.mark.parametrize("block,search,w,h,noise", [(16, 16, 640, 360, 1), (16, 8, 400, 200, 0), (8, 16, 328, 136, 2), (8, 8, 264, 72, 0)])
+def test_sea_half_height_tiles(emu, oracle, block, search, w, h, noise):
+    """The 32-row tile instances (launches that do not fill the machine)."""
+    prev, cur, _ = synth.make_pair(w, h, search, index=5, noise_lsb=noise)
+    check(emu, oracle, prev, cur, block, search, min_resolved=0.5, tile_h=32)
 
 
 def test_sea_ties_and_flat(emu, oracle):
@@ -132,7 +139,7 @@ def test_sea_strips(emu, oracle):
     prev, cur, _ = synth.make_pair(384, 272, 16, index=7, noise_lsb=1)
     omv, ocost, _ = oracle.block_match(prev, cur, 16, 16, 0, threads=oracle.max_threads(), fast=True)
     for y0, rows in ((0, 96), (96, 96), (192, 80)):
-        mv, cost, ent, res, _ = run_sea(emu, prev, cur, 16, 16, strip=(y0, rows))
+        mv, cost, ent, res, _ = run_sea(emu, prev, cur, 16, 16, strip=(y0, rows), tile_h=32 if y0 else 64)
         sl = slice(y0 // 16, (y0 + rows) // 16)
         r = res[0]
         np.testing.assert_array_equal(cost[0][r], ocost[sl][r])
