@@ -28,6 +28,7 @@
 // exhaustive kernels and to the oracle; only the amount of work is data-dependent.  Predictors change the work, never
 // the result: a candidate is dropped only when its (bound, position) key is not below an exact key already found.
 #ifndef OFPSB_EMU
+#include <cstdlib>
 #include "tma_common.cuh"
 #else
 #include "block_match_common.cuh"
@@ -57,13 +58,17 @@ struct SeaCfg {
     static constexpr int PW = SEA_TILE_W + 2 * RA;        // previous-frame window: bytes per row
     static constexpr int PH = TH + 2 * R;
     static constexpr int CW = SEA_TILE_W, CH = TH;
-    static constexpr int WC = PW / 2;                     // window-sum plane: u32 (= two u16 sums) per row
+    // pitch of the window-sum plane in u16: 84 words per row instead of 80, so that a COLUMN walk (lanes <-> dy: the best's
+    // own column in the zero-cost scan, the dx = +R column of the full scan) hits 8 different banks instead of 2
+    // (ncu r2: 44 % of the kernel's shared-load wavefronts were bank-conflict replays and the LSU pipe was its co-limiter)
+    static constexpr int SP = PW + 8;
+    static constexpr int WC = SP / 2;                     // window-sum plane: u32 (= two u16 sums) per row
     static constexpr int OR = PH - N + 1;                 // rows of window sums
     static constexpr int NSEG = SEA_NT / WC;              // row segments of the vertical pass
     static constexpr int SR = (OR + NSEG - 1) / NSEG;     // output rows per segment
     static constexpr int HR = (NSEG * SR + N - 1) > PH ? (NSEG * SR + N - 1) : PH;   // plane rows incl. slack
     static constexpr int P_BYTES = (PW * PH + 16 + 127) & ~127;   // +16: the last words read straddle the end
-    static constexpr int S_BYTES = (PW * 2 * HR + 127) & ~127;
+    static constexpr int S_BYTES = (SP * 2 * HR + 127) & ~127;
     static constexpr int C_BYTES = (CW * CH + 127) & ~127;
     static constexpr int SMEM_BYTES = P_BYTES + S_BYTES + C_BYTES + 128;   // + alignment slack
     static constexpr uint32_t TX_BYTES = (uint32_t)(PW * PH + CW * CH);
@@ -85,7 +90,7 @@ __device__ __forceinline__ uint32_t sea_pos(int dx, int dy, int R)
 
 // ---- step 2: N x N window sums of the staged window, in shared memory ------------------------------------------------
 // horizontal: H[y][x] = sum of N bytes of row y starting at x, four x per thread from two / three aligned words
-template <int N, int PW, int PH>
+template <int N, int PW, int PH, int SP>
 __device__ __forceinline__ void sea_hpass(const uint8_t* __restrict__ sP, uint32_t* __restrict__ sS, int tid)
 {
     // one item = 16 consecutive positions of one row: one 16-byte load + the one / two words behind it
@@ -123,7 +128,7 @@ __device__ __forceinline__ void sea_hpass(const uint8_t* __restrict__ sP, uint32
             o[2 * g] = h0 | (h1 << 16);
             o[2 * g + 1] = h2 | (h3 << 16);
         }
-        uint4* dst = reinterpret_cast<uint4*>(sS + row * (PW / 2) + 8 * k);
+        uint4* dst = reinterpret_cast<uint4*>(sS + row * (SP / 2) + 8 * k);
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
     }
@@ -213,40 +218,65 @@ struct SeaOut {
     int peer, own_rows, up_rows, has_up, has_down;
 };
 
+// The current tile is staged as [16-byte column block][row][16 bytes] (transposing tensor map, tma_common.cuh): the rows of
+// one block are contiguous, so the loads below are conflict-free.  (Row-major staging put the 16 rows of a block on the
+// same four banks: a 16-way conflict on every block's first load.)
 // current block -> registers: 8 (B=16) / 4 (B=8, lanes 0..15) bytes per lane, lane = 2 * row + half
-template <int B, int CW>
+template <int B, int CH>
 __device__ __forceinline__ void sea_cur_block(const uint8_t* __restrict__ sC, int bxl, int byl, int lane, uint32_t& c0,
                                               uint32_t& c1)
 {
     c0 = c1 = 0;
     if (B == 16) {
-        const uint2 v = *reinterpret_cast<const uint2*>(sC + (byl * B + (lane >> 1)) * CW + bxl * B + 8 * (lane & 1));
+        const uint2 v = *reinterpret_cast<const uint2*>(sC + (bxl * CH + byl * 16) * 16 + 8 * lane);
         c0 = v.x;
         c1 = v.y;
     } else if (lane < 16) {
-        c0 = *reinterpret_cast<const uint32_t*>(sC + (byl * B + (lane >> 1)) * CW + bxl * B + 4 * (lane & 1));
+        c0 = *reinterpret_cast<const uint32_t*>(sC + ((bxl >> 1) * CH + byl * 8 + (lane >> 1)) * 16 + (bxl & 1) * 8 + 4 * (lane & 1));
     }
 }
 
-// the four N x N sub-block sums of every block of the current tile -> s_csum[block] = (C00, C10, C01, C11)
+// the four N x N sub-block sums of every block of the current tile -> s_csum[block] = (C00, C10, C01, C11).
+// One thread per 16-byte row chunk (consecutive lanes = consecutive rows = consecutive chunks), rows folded by shuffles.
 template <typename C, int B>
 __device__ __forceinline__ void sea_cur_sums(const uint8_t* __restrict__ sC, uint32_t* __restrict__ s_csum, int tid)
 {
-    constexpr int N = C::N;
-    for (int i = tid; i < 4 * C::TBX * C::TBY; i += SEA_NT) {
-        const int blk = i >> 2, k = i & 3, bxl = blk % C::TBX, byl = blk / C::TBX;
-        const uint8_t* src = sC + (byl * B + (k >> 1) * N) * C::CW + bxl * B + (k & 1) * N;
-        uint32_t v = 0;
+    constexpr int CH = C::CH, NCB = C::CW / 16;
+    static_assert((NCB * CH) % 32 == 0 && CH % 16 == 0, "whole warps per pass, whole blocks per column");
+    for (int i = tid; i < NCB * CH; i += SEA_NT) {
+        const int cb = i / CH, row = i - cb * CH;
+        const uint4 w = *reinterpret_cast<const uint4*>(sC + (size_t)i * 16);
+        if (B == 16) {   // chunk = one row of block (cb, row / 16): left / right 8 bytes
+            uint32_t l = __dp4a(w.x, 0x01010101u, __dp4a(w.y, 0x01010101u, 0u));
+            uint32_t r = __dp4a(w.z, 0x01010101u, __dp4a(w.w, 0x01010101u, 0u));
 #pragma unroll
-        for (int r = 0; r < N; r++) {
-            if (N == 8) {
-                const uint2 w = *reinterpret_cast<const uint2*>(src + r * C::CW);
-                v = __dp4a(w.x, 0x01010101u, __dp4a(w.y, 0x01010101u, v));
-            } else {
-                v = __dp4a(*reinterpret_cast<const uint32_t*>(src + r * C::CW), 0x01010101u, v);
+            for (int o = 1; o < 8; o <<= 1) {
+                l += __shfl_xor_sync(0xffffffffu, l, o);
+                r += __shfl_xor_sync(0xffffffffu, r, o);
+            }
+            if ((row & 7) == 0) {
+                const int blk = (row >> 4) * C::TBX + cb, j = (row >> 3) & 1;
+                s_csum[4 * blk + 2 * j] = l;
+                s_csum[4 * blk + 2 * j + 1] = r;
+            }
+        } else {         // chunk = one row of blocks (2 cb, row / 8) and (2 cb + 1, row / 8): four 4-byte pieces
+            uint32_t s0 = __dp4a(w.x, 0x01010101u, 0u), s1 = __dp4a(w.y, 0x01010101u, 0u);
+            uint32_t s2 = __dp4a(w.z, 0x01010101u, 0u), s3 = __dp4a(w.w, 0x01010101u, 0u);
+#pragma unroll
+            for (int o = 1; o < 4; o <<= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+            }
+            if ((row & 3) == 0) {
+                const int blk = (row >> 3) * C::TBX + 2 * cb, j = (row >> 2) & 1;
+                s_csum[4 * blk + 2 * j] = s0;
+                s_csum[4 * blk + 2 * j + 1] = s1;
+                s_csum[4 * (blk + 1) + 2 * j] = s2;
+                s_csum[4 * (blk + 1) + 2 * j + 1] = s3;
             }
         }
-        s_csum[i] = v;
     }
 }
 
@@ -265,28 +295,34 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
                                                uint32_t pred, int lane, uint32_t* __restrict__ s_list, const SeaOut& out)
 {
     using C = SeaCfg<B, R, TH>;
-    constexpr int N = C::N, ND = C::ND, PW = C::PW, CW = C::CW;
+    constexpr int N = C::N, ND = C::ND, PW = C::PW, SP = C::SP;
     constexpr uint32_t NONE = 0xFFFFFFFFu;
-    const int x0 = bx * B, y0 = by * B;
-    const int dy_lo = max(-R, -p.halo_top - y0), dy_hi = min(R, p.strip_h + p.halo_bottom - B - y0);
-    const int dx_lo = max(-R, -x0), dx_hi = min(R, p.w - B - x0);
+    int dy_lo = -R, dy_hi = R, dx_lo = -R, dx_hi = R;        // interior tiles (warp-uniform): every candidate is legal
+    if (!interior) {
+        const int x0 = bx * B, y0 = by * B;
+        dy_lo = max(-R, -p.halo_top - y0);
+        dy_hi = min(R, p.strip_h + p.halo_bottom - B - y0);
+        dx_lo = max(-R, -x0);
+        dx_hi = min(R, p.w - B - x0);
+    }
     const int wx0 = bxl * B + C::RA, wy0 = byl * B + R;      // block origin in window coordinates
     const int dx = lane - R;                                  // lanes <-> dx mapping
     const bool lane_in = lane < C::NL && dx >= dx_lo && dx <= dx_hi;
 
     uint32_t c0, c1;
-    sea_cur_block<B, CW>(sC, bxl, byl, lane, c0, c1);
+    sea_cur_block<B, C::CH>(sC, bxl, byl, lane, c0, c1);
     const uint4 csum = *reinterpret_cast<const uint4*>(s_csum + 4 * (byl * C::TBX + bxl));
     const uint32_t C00 = csum.x, C10 = csum.y, C01 = csum.z, C11 = csum.w;
 
     // ---- a. exact cost of the predictor; of the zero vector too unless the predictor already matches exactly (the
     // zero vector is then one of the shorter candidates step b rules out by their window sums)
     const uint32_t pos00 = sea_pos(0, 0, R);
-    {
-        const int pdx = (int)(pred & 127u) - R, pdy = (int)((pred >> 7) & 127u) - R;
-        if (pdx < dx_lo || pdx > dx_hi || pdy < dy_lo || pdy > dy_hi) pred = pos00;
+    int pdx = (int)(pred & 127u) - R, pdy = (int)((pred >> 7) & 127u) - R;
+    if (!interior && (pdx < dx_lo || pdx > dx_hi || pdy < dy_lo || pdy > dy_hi)) {
+        pred = pos00;
+        pdx = pdy = 0;
     }
-    uint32_t bc = sea_exact<B, PW>(sP, wx0 + (int)(pred & 127u) - R, wy0 + (int)((pred >> 7) & 127u) - R, c0, c1, lane);
+    uint32_t bc = sea_exact<B, PW>(sP, wx0 + pdx, wy0 + pdy, c0, c1, lane);
     uint32_t bp = pred;
     unsigned long long evaluated = 1;
     uint32_t zpos = pred == pos00 ? pos00 : NONE;             // pos00 once the zero vector has been evaluated
@@ -296,15 +332,17 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
         zpos = pos00;
         if (c < bc || (c == bc && pos00 < bp)) { bc = c; bp = pos00; }
     }
-    const uint16_t* scol = sS + byl * B * PW + wx0 - R + lane;   // window sum at (dx = lane - R, dy = -R)
+    const uint16_t* scol = sS + byl * B * SP + wx0 - R + lane;   // window sum at (dx = lane - R, dy = -R)
     bool resolved = true, full_scan = false;
 
     if (bc == 0) {
         // ---- b. a zero-cost match: only a zero-cost candidate with a smaller position code (a shorter vector) wins
         if (bp != pos00) {
             const int d2 = (int)(bp >> 14);
-            const int bdx = (int)(bp & 127u) - R, bdy = (int)((bp >> 7) & 127u) - R;
-            const int r = (int)sqrtf((float)d2);   // correctly rounded f32 sqrt of an integer < 2^13: floor is exact
+            const int bdx = pdx, bdy = pdy;        // a zero-cost best other than the zero vector is the predictor
+            // floor(sqrt(d2)): at least max(|dx|, |dy|), a few steps above it at most
+            int r = max(abs(bdx), abs(bdy));
+            while ((r + 1) * (r + 1) <= d2) r++;
             const int ya = max(-r, dy_lo), yb = min(r, dy_hi);
             // a window sum is < 2^16: idle lanes never match.  The best's own position always matches, so its column
             // is left out of the row scan and tested on its own below.
@@ -313,15 +351,15 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
             // the exact cost only where a first sub-sum matches.  Rows past yb are inside the plane (G - 1 <= N) and
             // are masked in the slow path.
             constexpr int G = N >= 8 ? 8 : 4;
-            const uint16_t* qg = scol + (ya + R) * PW;
-            for (int dyq = ya; dyq <= yb; dyq += G, qg += G * PW) {
+            const uint16_t* qg = scol + (ya + R) * SP;
+            for (int dyq = ya; dyq <= yb; dyq += G, qg += G * SP) {
                 bool any = false;
 #pragma unroll
-                for (int j = 0; j < G; j++) any |= (uint32_t)qg[j * PW] == c00l;
+                for (int j = 0; j < G; j++) any |= (uint32_t)qg[j * SP] == c00l;
                 if (__ballot_sync(0xffffffffu, any) == 0u) continue;
                 uint32_t code = 0;
 #pragma unroll
-                for (int j = 0; j < G; j++) code |= ((uint32_t)qg[j * PW] == c00l ? 1u : 0u) << j;
+                for (int j = 0; j < G; j++) code |= ((uint32_t)qg[j * SP] == c00l ? 1u : 0u) << j;
                 const int nrow = yb - dyq + 1;
                 if (nrow < G) code &= (1u << nrow) - 1u;
                 unsigned rows = __reduce_or_sync(0xffffffffu, code);
@@ -329,10 +367,10 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
                     const int j = __ffs(rows) - 1;
                     rows &= rows - 1;
                     const int dy = dyq + j;
-                    const uint16_t* q = qg + j * PW;
+                    const uint16_t* q = qg + j * SP;
                     const uint32_t pos = sea_pos(dx, dy, R);
-                    const bool zero = ((code >> j) & 1u) && pos < bp && (uint32_t)q[N] == C10 && (uint32_t)q[N * PW] == C01 &&
-                                      (uint32_t)q[N * PW + N] == C11;
+                    const bool zero = ((code >> j) & 1u) && pos < bp && (uint32_t)q[N] == C10 && (uint32_t)q[N * SP] == C01 &&
+                                      (uint32_t)q[N * SP + N] == C11;
                     unsigned m = __ballot_sync(0xffffffffu, zero);
                     while (m) {
                         const int l = __ffs(m) - 1;
@@ -346,17 +384,17 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
                 }
             }
             {   // the best's own column (its vector may have changed above: `bdx` is the column left out), lanes <-> dy
-                const uint16_t* col = sS + (byl * B + R) * PW + wx0 + bdx;
+                const uint16_t* col = sS + (byl * B + R) * SP + wx0 + bdx;
 #pragma unroll
                 for (int t = 0; t < (2 * R + 1 + 31) / 32; t++) {
                     if (t > 0 && ya + 32 * t > yb) break;
                     const int dy = ya + lane + 32 * t;
-                    const uint16_t* q = col + min(dy, yb) * PW;
+                    const uint16_t* q = col + min(dy, yb) * SP;
                     const uint32_t pos = sea_pos(bdx, dy, R);
                     const bool hit = dy <= yb && dy != bdy && (uint32_t)q[0] == C00;
                     if (__ballot_sync(0xffffffffu, hit) == 0u) continue;
-                    const bool zero = hit && pos < bp && (uint32_t)q[N] == C10 && (uint32_t)q[N * PW] == C01 &&
-                                      (uint32_t)q[N * PW + N] == C11;
+                    const bool zero = hit && pos < bp && (uint32_t)q[N] == C10 && (uint32_t)q[N * SP] == C01 &&
+                                      (uint32_t)q[N * SP + N] == C11;
                     unsigned m = __ballot_sync(0xffffffffu, zero);
                     while (m) {
                         const int l = __ffs(m) - 1;
@@ -374,10 +412,10 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
                 for (int t = 0; t < (C::NEX > 0 ? C::NEX : 1); t++) {
                     const int dyi = lane + 32 * t, dy = dyi - R;
                     const bool ok = dyi < ND && dy >= dy_lo && dy <= dy_hi;
-                    const uint16_t* q = sS + (byl * B + (ok ? dyi : 0)) * PW + wx0 + R;
+                    const uint16_t* q = sS + (byl * B + (ok ? dyi : 0)) * SP + wx0 + R;
                     const uint32_t pos = sea_pos(R, dy, R);
                     const bool zero = ok && pos < bp && (uint32_t)q[0] == C00 && (uint32_t)q[N] == C10 &&
-                                      (uint32_t)q[N * PW] == C01 && (uint32_t)q[N * PW + N] == C11;
+                                      (uint32_t)q[N * SP] == C01 && (uint32_t)q[N * SP + N] == C11;
                     unsigned m = __ballot_sync(0xffffffffu, zero);
                     while (m) {
                         const int l = __ffs(m) - 1;
@@ -398,7 +436,7 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
         uint32_t b[ND];
 #pragma unroll
         for (int t = 0; t < ND + N; t++) {
-            const uint32_t sa = scol[t * PW], sb = scol[t * PW + N];
+            const uint32_t sa = scol[t * SP], sb = scol[t * SP + N];
             if (t < ND) b[t] = __usad(sb, C10, __usad(sa, C00, 0u));
             if (t >= N) b[t - N] = __usad(sb, C11, __usad(sa, C01, b[t - N]));
         }
@@ -413,8 +451,8 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
             for (int t = 0; t < C::NEX; t++) {
                 const int dyi = lane + 32 * t, dy = dyi - R;
                 const bool ok = dyi < ND && dy >= dy_lo && dy <= dy_hi && R <= dx_hi;
-                const uint16_t* q = sS + (byl * B + (dyi < ND ? dyi : 0)) * PW + wx0 + R;
-                const uint32_t v = __usad(q[N * PW + N], C11, __usad(q[N * PW], C01, __usad(q[N], C10, __usad(q[0], C00, 0u))));
+                const uint16_t* q = sS + (byl * B + (dyi < ND ? dyi : 0)) * SP + wx0 + R;
+                const uint32_t v = __usad(q[N * SP + N], C11, __usad(q[N * SP], C01, __usad(q[N], C10, __usad(q[0], C00, 0u))));
                 bex[t] = ok ? v : SEA_BIG;
             }
         }
@@ -486,8 +524,8 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
                     const uint32_t pos = sea_pos(dxi - R, dyi - R, R);
                     if (pos == zpos || pos == pred || pos == pos_min) continue;   // already evaluated
                     if (bc == 0 && pos > bp) continue;
-                    const uint16_t* q = sS + (byl * B + dyi) * PW + wx0 - R + dxi;
-                    const uint32_t lb = __usad(q[N * PW + N], C11, __usad(q[N * PW], C01, __usad(q[N], C10, __usad(q[0], C00, 0u))));
+                    const uint16_t* q = sS + (byl * B + dyi) * SP + wx0 - R + dxi;
+                    const uint32_t lb = __usad(q[N * SP + N], C11, __usad(q[N * SP], C01, __usad(q[N], C10, __usad(q[0], C00, 0u))));
                     if (!(lb < bc || (lb == bc && pos < bp))) continue;           // the best tightened meanwhile
                     const uint32_t c = sea_exact<B, PW>(sP, wx0 + dxi - R, wy0 + dyi - R, c0, c1, lane);
                     evaluated++;
@@ -560,7 +598,7 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
         } else {
             tma_load_3d(smem_u32(sP), &maps.prev, wx, wy, pair, b32);
         }
-        tma_load_3d(smem_u32(sC), &maps.cur, tx0, ty0, pair, b32);
+        tma_load_4d(smem_u32(sC), &maps.cur, 0, ty0, tx0 / 16, pair, b32);
         // the frames stream through the L2 once: pull the boxes of the tile a CTA that starts about one wave later will
         // load into the L2 now, so that its loads do not wait for HBM
         if (out.prefetch_tiles > 0) {
@@ -570,7 +608,7 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
             if (tz < gridDim.z) {
                 const int py = (int)(trem / gridDim.x), px = (int)(trem - (unsigned)py * gridDim.x);
                 tma_prefetch_3d(&maps.prev, px * SEA_TILE_W - C::RA, py * TH - R + (out.peer ? 0 : p.halo_top), (int)tz);
-                tma_prefetch_3d(&maps.cur, px * SEA_TILE_W, py * TH, (int)tz);
+                tma_prefetch_4d(&maps.cur, 0, py * TH, px * (SEA_TILE_W / 16), (int)tz);
             }
         }
     }
@@ -587,14 +625,15 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
             const int y = wy + i / C::PW, x = wx + i % C::PW;
             sP[i] = (x >= 0 && x < p.w && y >= 0 && y < rows_prev) ? pb[(long long)y * p.stride + x] : 0;
         }
-        for (int i = tid; i < C::CW * C::CH; i += SEA_NT) {
-            const int y = ty0 + i / C::CW, x = tx0 + i % C::CW;
-            sC[i] = (x < p.w && y < p.strip_h) ? cb[(long long)y * p.stride + x] : 0;
+        for (int i = tid; i < C::CW * C::CH; i += SEA_NT) {   // [column block][row][16]; whole column blocks of the tensor
+            const int c16 = i / (C::CH * 16), row = (i / 16) % C::CH, b = i % 16;
+            const int y = ty0 + row, x = tx0 + c16 * 16 + b;
+            sC[i] = (tx0 / 16 + c16 < (p.w + 15) / 16 && y < p.strip_h) ? cb[(long long)y * p.stride + x] : 0;
         }
     }
     __syncthreads();
 #endif
-    sea_hpass<C::N, C::PW, C::PH>(sP, sS32, tid);
+    sea_hpass<C::N, C::PW, C::PH, C::SP>(sP, sS32, tid);
     sea_cur_sums<C, B>(sC, s_csum, tid);
     __syncthreads();
     sea_vpass<C>(sS32, tid);
@@ -610,15 +649,15 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
     // (a few candidates per thread).  It only seeds the first block of every warp — a predictor changes the work,
     // never the result — and replaces a full scan per warp and tile (ncu: a quarter of all blocks before this).
     {
-        constexpr int N = C::N, ND = C::ND, PW = C::PW;
+        constexpr int N = C::N, ND = C::ND, SP = C::SP;
         const uint4 cs = *reinterpret_cast<const uint4*>(s_csum);
         const int dy_lo = max(-R, -p.halo_top - ty0), dy_hi = min(R, p.strip_h + p.halo_bottom - B - ty0);
         const int dx_lo = max(-R, -tx0), dx_hi = min(R, p.w - B - tx0);
         uint32_t kb = 0xFFFFFFFFu;
         for (int idx = tid; idx < ND * ND; idx += SEA_NT) {
             const int dyi = idx / ND, dxi = idx - dyi * ND;
-            const uint16_t* q = sS + dyi * PW + C::RA - R + dxi;
-            const uint32_t v = __usad(q[N * PW + N], cs.w, __usad(q[N * PW], cs.z, __usad(q[N], cs.y, __usad(q[0], cs.x, 0u))));
+            const uint16_t* q = sS + dyi * SP + C::RA - R + dxi;
+            const uint32_t v = __usad(q[N * SP + N], cs.w, __usad(q[N * SP], cs.z, __usad(q[N], cs.y, __usad(q[0], cs.x, 0u))));
             const bool ok = interior || (dxi - R >= dx_lo && dxi - R <= dx_hi && dyi - R >= dy_lo && dyi - R <= dy_hi);
             if (ok) kb = min(kb, (v << 12) | (uint32_t)idx);
         }
@@ -682,13 +721,18 @@ int launch_sea_th(const BlockMatchParams& p, const SeaOut& out, const SeaPeer* p
         if (!make_map(&maps.prev, prev_base, p.w, rows_prev, p.stride, p.pair_stride, p.n_pairs, C::PW, C::PH)) return 1;
         maps.prev8 = maps.up8 = maps.down8 = maps.prev;
     }
-    if (!make_map(&maps.cur, p.cur, p.w, p.strip_h, p.stride, p.pair_stride, p.n_pairs, C::CW, C::CH)) return 1;
+    if (!make_map_colblocks(&maps.cur, p.cur, p.w, p.strip_h, p.stride, p.pair_stride, p.n_pairs, C::CH, C::CW / 16)) return 1;
     static bool attr_set[64] = {};
     int dev = 0;
     OFPSB_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         OFPSB_CUDA_TRY(cudaFuncSetAttribute(sea_kernel<B, R, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    if (getenv("OFPSB_DEBUG_OCC")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sea_kernel<B, R, TH>, SEA_NT, C::SMEM_BYTES);
+        fprintf(stderr, "sea_kernel<%d,%d,%d>: %d CTAs/SM, %d B dynamic smem\n", B, R, TH, nb, C::SMEM_BYTES);
     }
     const dim3 grid((p.nbx * B + SEA_TILE_W - 1) / SEA_TILE_W, (p.nby * B + TH - 1) / TH, p.n_pairs);
     sea_kernel<B, R, TH><<<grid, SEA_NT, C::SMEM_BYTES, stream>>>(maps, p, out);
