@@ -327,15 +327,16 @@ def run_ours(args):
     out = np.empty((NBLOCKS, 4), np.float32)
     last = None
 
-    def frame_pass(pipelined):
+    def frame_pass(pipelined, src=None):
         nonlocal last
+        src = pageable if src is None else src
         n_out = 0
         for i in range(PAIRS + 1):
             if pipelined:
-                st.submit(pageable[i])
+                st.submit(src[i])
                 if i >= 3 and st.collect(out) is not None:
                     n_out += 1
-            elif st.push(pageable[i], out) is not None:
+            elif st.push(src[i], out) is not None:
                 n_out += 1
         while pipelined and st.collect(out) is not None:
             n_out += 1
@@ -351,12 +352,18 @@ def run_ours(args):
     t0 = time.perf_counter()
     n_sync = frame_pass(False)
     t_sync = time.perf_counter() - t0
+    frame_pass(True, host.array)
+    barrier()
+    t0 = time.perf_counter()
+    n_pin = frame_pass(True, host.array)                           # page-locked caller frames: no staging copy
+    t_pin = time.perf_counter() - t0
+    frame_pass(True)                                               # leave `last` = result of a pageable pass
     st.close()
     # (every pass restarts the stream at frame 0 after frame PAIRS: that extra pair is counted, its result unused)
     if last.tobytes() != host_entries.array[PAIRS - 1].tobytes():
         raise SystemExit("bench.py: streaming-API and batch-API results differ")
-    dev_ms, e2e_ms, exh_ms, noisy_ms, sea_ms, list_ms, t_pipe, t_sync = rank_max(dev_ms, e2e_ms, exh_ms, noisy_ms, sea_ms, list_ms,
-                                                                                 t_pipe, t_sync)
+    dev_ms, e2e_ms, exh_ms, noisy_ms, sea_ms, list_ms, t_pipe, t_sync, t_pin = rank_max(dev_ms, e2e_ms, exh_ms, noisy_ms, sea_ms,
+                                                                                        list_ms, t_pipe, t_sync, t_pin)
 
     extra = {}
     if world > 1:
@@ -396,9 +403,11 @@ def run_ours(args):
                     "api": "ofpsb_block_match_batch (pinned host frames -> MotionEntry lists)"},
             "e2e_frame": {"value": W * H * n_pipe * world / t_pipe / 1e6, "unit": "Mpix/s", "frames_per_s_per_gpu": n_pipe / t_pipe,
                           "sync_push": {"value": W * H * n_sync * world / t_sync / 1e6, "us_per_frame": 1e6 * t_sync / n_sync},
+                          "pinned_frames": {"value": W * H * n_pin * world / t_pin / 1e6, "us_per_frame": 1e6 * t_pin / n_pin},
                           "h2d_bytes_per_frame": frame_bytes, "d2h_bytes_per_frame": NBLOCKS * 16,
                           "api": "ofpsb_stream_submit / _collect, one PAGEABLE 1080p frame per call (the drop-in Decoder path); "
-                                 "sync_push = ofpsb_stream_push, result returned by the same call"},
+                                 "sync_push = ofpsb_stream_push, result returned by the same call; pinned_frames = the "
+                                 "pipelined form on page-locked caller frames (no staging copy)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_SEA_STEP, "peak_source": peak_src,

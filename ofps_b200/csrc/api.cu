@@ -66,6 +66,38 @@ void PinBuf::release()
     cap = 0;
 }
 
+// The block-matching dispatch of a context on a given scratch / stream (the streaming decoder alternates two of each so
+// that consecutive pairs overlap on the device).
+int launch_block_match_ctx(ofpsb_ctx* ctx, const BlockMatchParams& p, BlockMatchScratch& scratch, cudaStream_t stream)
+{
+    // grid.z carries the pair index: split very large batches
+    const size_t nb = (size_t)p.nbx * p.nby;
+    for (int first = 0; first < p.n_pairs; first += 32768) {
+        BlockMatchParams q = p;
+        q.n_pairs = p.n_pairs - first < 32768 ? p.n_pairs - first : 32768;
+        q.prev = p.prev + (long long)first * p.pair_stride;
+        q.cur = p.cur + (long long)first * p.pair_stride;
+        if (p.mv_xy) q.mv_xy = p.mv_xy + 2 * nb * first;
+        if (p.cost) q.cost = p.cost + nb * first;
+        if (p.entries) q.entries = p.entries + nb * first;
+        int rc = 1;
+        if (ctx->opt_block_match_prune && ctx->opt_block_match_kernel == 0)
+            rc = launch_block_match_pruned(q, scratch, ctx->sm_count, stream, &ctx->launches);
+        if (rc != 1) {
+            if (rc) return rc;
+            continue;
+        }
+        switch (ctx->opt_block_match_kernel) {
+            case 1: rc = launch_block_match_generic(q, stream, &ctx->launches); break;
+            case 2: rc = launch_block_match_ldg(q, stream, &ctx->launches); break;
+            case 3: rc = launch_block_match(q, stream, &ctx->launches, 1); break;
+            default: rc = launch_block_match(q, stream, &ctx->launches, 0); break;
+        }
+        if (rc) return rc;
+    }
+    return OFPSB_OK;
+}
+
 namespace {
 
 int get_event(ofpsb_ctx* ctx, size_t idx, cudaEvent_t* out)
@@ -109,35 +141,7 @@ int fill_params(BlockMatchParams& p, const uint8_t* d_prev, const uint8_t* d_cur
     return OFPSB_OK;
 }
 
-int launch_bm(ofpsb_ctx* ctx, const BlockMatchParams& p)
-{
-    // grid.z carries the pair index: split very large batches
-    const size_t nb = (size_t)p.nbx * p.nby;
-    for (int first = 0; first < p.n_pairs; first += 32768) {
-        BlockMatchParams q = p;
-        q.n_pairs = p.n_pairs - first < 32768 ? p.n_pairs - first : 32768;
-        q.prev = p.prev + (long long)first * p.pair_stride;
-        q.cur = p.cur + (long long)first * p.pair_stride;
-        if (p.mv_xy) q.mv_xy = p.mv_xy + 2 * nb * first;
-        if (p.cost) q.cost = p.cost + nb * first;
-        if (p.entries) q.entries = p.entries + nb * first;
-        int rc = 1;
-        if (ctx->opt_block_match_prune && ctx->opt_block_match_kernel == 0)
-            rc = launch_block_match_pruned(q, ctx->bm_scratch, ctx->sm_count, ctx->stream, &ctx->launches);
-        if (rc != 1) {
-            if (rc) return rc;
-            continue;
-        }
-        switch (ctx->opt_block_match_kernel) {
-            case 1: rc = launch_block_match_generic(q, ctx->stream, &ctx->launches); break;
-            case 2: rc = launch_block_match_ldg(q, ctx->stream, &ctx->launches); break;
-            case 3: rc = launch_block_match(q, ctx->stream, &ctx->launches, 1); break;
-            default: rc = launch_block_match(q, ctx->stream, &ctx->launches, 0); break;
-        }
-        if (rc) return rc;
-    }
-    return OFPSB_OK;
-}
+int launch_bm(ofpsb_ctx* ctx, const BlockMatchParams& p) { return launch_block_match_ctx(ctx, p, ctx->bm_scratch, ctx->stream); }
 
 size_t block_dim_host(float min_size, size_t subdivide)
 {

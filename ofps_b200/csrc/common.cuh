@@ -207,6 +207,8 @@ struct ofpsb_ctx {
 
 #ifndef OFPSB_EMU
 namespace ofpsb {
+int launch_block_match_ctx(ofpsb_ctx* ctx, const BlockMatchParams& p, BlockMatchScratch& scratch, cudaStream_t stream);
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;

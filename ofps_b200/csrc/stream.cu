@@ -115,6 +115,10 @@ struct ofpsb_stream {
     uint8_t* h_frames = nullptr;       // depth pinned staging frames
     ofps_mv* h_entries = nullptr;      // depth pinned entry lists
     std::vector<cudaEvent_t> h2d_done, comp_done, d2h_done;
+    // consecutive pairs are independent and one 1080p pair fills half the machine: they alternate between two compute
+    // streams (each with its own work-list scratch) so that pair k+1 runs beside pair k
+    cudaStream_t comp[2] = {nullptr, nullptr};
+    BlockMatchScratch scratch[2];
     long long submitted = 0;           // frames submitted
     long long collected = 0;           // pairs collected (pair j = frames j, j+1)
     CopyPool* pool = nullptr;
@@ -128,6 +132,16 @@ void ofpsb_stream_close(ofpsb_stream* s)
     if (!s) return;
     DeviceGuard guard(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    if (s->comp[1]) {
+        cudaStreamSynchronize(s->comp[1]);
+        cudaStreamDestroy(s->comp[1]);
+    }
+    for (auto& sc : s->scratch) {
+        sc.sums.release();
+        sc.worklist.release();
+        if (sc.ev_listed) cudaEventDestroy(sc.ev_listed);
+        if (sc.h_listed) cudaFreeHost(sc.h_listed);
+    }
     cudaStreamSynchronize(s->ctx->copy_stream);
     cudaStreamSynchronize(s->ctx->d2h_stream);
     delete s->pool;
@@ -163,6 +177,8 @@ int ofpsb_stream_open(ofpsb_ctx* ctx, int w, int h, int block, int range, int me
     if (e == cudaSuccess) e = cudaMalloc(&s->d_entries, ent_bytes * s->depth);
     if (e == cudaSuccess) e = cudaHostAlloc(&s->h_frames, s->frame_bytes * s->depth, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(&s->h_entries, ent_bytes * s->depth, cudaHostAllocDefault);
+    s->comp[0] = ctx->stream;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->comp[1], cudaStreamNonBlocking);
     for (auto* v : {&s->h2d_done, &s->comp_done, &s->d2h_done})
         for (int i = 0; i < s->depth && e == cudaSuccess; i++) {
             cudaEvent_t ev = nullptr;
@@ -175,8 +191,9 @@ int ofpsb_stream_open(ofpsb_ctx* ctx, int w, int h, int block, int range, int me
         return e == cudaErrorMemoryAllocation ? OFPSB_E_NOMEM : OFPSB_E_CUDA;
     }
     unsigned hc = std::thread::hardware_concurrency();
-    // a single core copies ~10 GB/s: a 2 MB frame needs several to stay below its PCIe time (a quarter of the cores, <= 7)
-    const int helpers = s->frame_bytes >= (1u << 20) ? (hc >= 8 ? (int)(hc / 4 > 7 ? 7 : hc / 4) : hc >= 4 ? 1 : 0) : 0;
+    // a single core copies ~7 GB/s on the pool's hosts: a 2 MB frame needs several to stay below its PCIe time (measured:
+    // 5 threads 61 us per 1080p frame against 40 us of H2D) — half the cores, at most 8 copy threads
+    const int helpers = s->frame_bytes >= (1u << 20) ? (hc >= 4 ? (int)(hc / 2 - 1 > 7 ? 7 : hc / 2 - 1) : 0) : 0;
     s->pool = new (std::nothrow) CopyPool(helpers);
     *out = s;
     return OFPSB_OK;
@@ -202,7 +219,11 @@ int ofpsb_stream_submit(ofpsb_stream* s, const uint8_t* frame, size_t stride)
     uint8_t* d_frame = s->d_frames + s->frame_bytes * slot;
     // device frame `slot` held frame k-depth: prev of pair k-depth (= frames k-depth, k-depth+1), computed after frame
     // k-depth+1 arrived — event comp_done[(k-depth+1) % depth]
-    if (k >= s->depth) OFPSB_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, s->comp_done[(size_t)((k - s->depth + 1) % s->depth)], 0));
+    if (k >= s->depth) {
+        // pair k-depth (frame k-depth as cur) and pair k-depth+1 (as prev) ran on different compute streams
+        OFPSB_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, s->comp_done[(size_t)slot], 0));
+        OFPSB_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, s->comp_done[(size_t)((k - s->depth + 1) % s->depth)], 0));
+    }
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, frame) == cudaSuccess &&
                         (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
@@ -218,24 +239,51 @@ int ofpsb_stream_submit(ofpsb_stream* s, const uint8_t* frame, size_t stride)
         OFPSB_CUDA_TRY(cudaMemcpyAsync(d_frame, stage, (size_t)s->stride * s->h, cudaMemcpyHostToDevice, ctx->copy_stream));
     }
     OFPSB_CUDA_TRY(cudaEventRecord(s->h2d_done[(size_t)slot], ctx->copy_stream));
-    OFPSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->h2d_done[(size_t)slot], 0));
+    cudaStream_t cs = s->comp[k & 1];
+    OFPSB_CUDA_TRY(cudaStreamWaitEvent(cs, s->h2d_done[(size_t)slot], 0));
     if (k > 0 && s->nb > 0) {
         const int pslot = (int)((k - 1) % s->depth);
-        ofps_mv* d_ent = reinterpret_cast<ofps_mv*>(reinterpret_cast<uint8_t*>(s->d_entries) +
-                                                    (((s->nb * sizeof(ofps_mv)) + 255) & ~(size_t)255) * slot);
-        ofps_mv* h_ent = reinterpret_cast<ofps_mv*>(reinterpret_cast<uint8_t*>(s->h_entries) +
-                                                    (((s->nb * sizeof(ofps_mv)) + 255) & ~(size_t)255) * slot);
-        // entry list `slot` was read back for pair k-1-depth: its D2H must have left before the kernels overwrite it
-        if (k >= s->depth) OFPSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->d2h_done[(size_t)slot], 0));
-        if (int rc = ofpsb_block_match_dev(ctx, s->d_frames + s->frame_bytes * pslot, d_frame, s->w, s->h, s->stride, 0, 1, s->block,
-                                           s->range, s->metric, nullptr, nullptr, d_ent))
-            return rc;
-        OFPSB_CUDA_TRY(cudaEventRecord(s->comp_done[(size_t)slot], ctx->stream));
+        const size_t ent_bytes = ((s->nb * sizeof(ofps_mv)) + 255) & ~(size_t)255;
+        ofps_mv* d_ent = reinterpret_cast<ofps_mv*>(reinterpret_cast<uint8_t*>(s->d_entries) + ent_bytes * slot);
+        ofps_mv* h_ent = reinterpret_cast<ofps_mv*>(reinterpret_cast<uint8_t*>(s->h_entries) + ent_bytes * slot);
+        // the previous frame was uploaded for the other compute stream; entry list `slot` was read back for pair
+        // k-1-depth: its D2H must have left before the kernels overwrite it
+        OFPSB_CUDA_TRY(cudaStreamWaitEvent(cs, s->h2d_done[(size_t)pslot], 0));
+        if (k >= s->depth) OFPSB_CUDA_TRY(cudaStreamWaitEvent(cs, s->d2h_done[(size_t)slot], 0));
+        BlockMatchParams p{};
+        p.prev = s->d_frames + s->frame_bytes * pslot;
+        p.cur = d_frame;
+        p.w = s->w;
+        p.strip_h = s->h;
+        p.stride = s->stride;
+        p.pair_stride = 0;
+        p.n_pairs = 1;
+        p.full_h = s->h;
+        p.block = s->block;
+        p.range = s->range;
+        p.metric = s->metric;
+        p.nbx = s->w / s->block;
+        p.nby = s->h / s->block;
+        p.entries = d_ent;
+        // statistics / profiling options address the context's own scratch: those launches stay on its stream
+        BlockMatchScratch& sc = (ctx->bm_scratch.collect_stats || ctx->bm_scratch.profile) ? ctx->bm_scratch : s->scratch[k & 1];
+        if (&sc == &ctx->bm_scratch) {
+            OFPSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->h2d_done[(size_t)slot], 0));
+            OFPSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->h2d_done[(size_t)pslot], 0));
+            if (k >= s->depth) OFPSB_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, s->d2h_done[(size_t)slot], 0));
+            cs = ctx->stream;
+        } else {
+            sc.pruner = ctx->bm_scratch.pruner;
+            sc.tile_h = ctx->bm_scratch.tile_h;
+            sc.adaptive = ctx->bm_scratch.adaptive;
+        }
+        if (int rc = launch_block_match_ctx(ctx, p, sc, cs)) return rc;
+        OFPSB_CUDA_TRY(cudaEventRecord(s->comp_done[(size_t)slot], cs));
         OFPSB_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, s->comp_done[(size_t)slot], 0));
         OFPSB_CUDA_TRY(cudaMemcpyAsync(h_ent, d_ent, s->nb * sizeof(ofps_mv), cudaMemcpyDeviceToHost, ctx->d2h_stream));
         OFPSB_CUDA_TRY(cudaEventRecord(s->d2h_done[(size_t)slot], ctx->d2h_stream));
     } else {
-        OFPSB_CUDA_TRY(cudaEventRecord(s->comp_done[(size_t)slot], ctx->stream));
+        OFPSB_CUDA_TRY(cudaEventRecord(s->comp_done[(size_t)slot], cs));
     }
     s->submitted = k + 1;
     return OFPSB_OK;
