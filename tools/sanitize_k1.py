@@ -1,0 +1,79 @@
+"""Target for compute-sanitizer (memcheck / racecheck) over the round-2 kernels: the fused SEA block matcher (both tile
+heights, every tuned geometry, frame borders, strips with peer halos, batch mode), the low-latency work-list instance, the
+streaming decoder, the one-warp detector, the staged-id densifier and the persistent Almeida grid; results are compared
+with the oracle as they go.
+
+    compute-sanitizer --tool memcheck  python tools/sanitize_k1.py
+    compute-sanitizer --tool racecheck python tools/sanitize_k1.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import oracle
+from ofps_b200 import capi, synth
+
+
+def main():
+    oracle.build()
+    ctx = capi.Context(0)
+    checks = 0
+    for (w, h, b, r, noise) in ((320, 144, 16, 16, 0), (336, 104, 16, 8, 1), (160, 72, 8, 16, 2), (168, 48, 8, 8, 0)):
+        prev, cur, _ = synth.make_pair(w, h, r, index=checks, noise_lsb=noise)
+        mv, cost, ent = oracle.block_match(prev, cur, b, r, 0, threads=oracle.max_threads(), fast=True)
+        for th in (64, 32):
+            ctx.set_option("block_match_tile_h", th)
+            got = ctx.block_match(prev, cur, b, r, 0)
+            assert np.array_equal(got["mv"], mv) and np.array_equal(got["cost"], cost) and got["entries"].tobytes() == ent.tobytes()
+            checks += 1
+        ctx.set_option("block_match_tile_h", 0)
+    # batch + strips with peer halos (three ranks on one device), stream batch
+    frames = synth.make_stream(4, 320, 176, 16, noise_lsb=1)
+    whole = ctx.block_match(frames[:-1], frames[1:], 16, 16, 0, want=("entries",))["entries"].reshape(3, -1, 4)
+    ts = [capi.Tiled(ctx, k, 3, 320, 176, 16, 16, 4) for k in range(3)]
+    for k, t in enumerate(ts):
+        t.connect_local(ts[k - 1] if k else None, ts[k + 1] if k < 2 else None)
+    for t in ts:
+        for s in range(4):
+            t.upload(s, frames[s, t.y0:t.y0 + t.own_rows])
+            t.publish(s)
+    parts = []
+    for t in ts:
+        de = ctx.dev_alloc(3 * t.n_blocks * 16)
+        for _ in range(3):
+            t.match_stream(0, 3, de)
+            t.match(1, 2, de)
+            t.match_stream(0, 3, de)
+        ctx.sync()
+        e = np.empty((3, t.n_blocks, 4), np.float32)
+        ctx.to_host(e, de)
+        ctx.dev_free(de)
+        parts.append(e)
+    assert np.concatenate(parts, axis=1).tobytes() == whole.tobytes()
+    for t in ts:
+        t.close()
+    checks += 1
+    # streaming decoder
+    st = capi.FrameStream(ctx, 320, 176, 16, 16, 0, depth=4)
+    assert st.push(frames[0]) is None
+    for i in range(1, 4):
+        assert st.push(frames[i]).tobytes() == whole[i - 1].tobytes()
+        checks += 1
+    st.close()
+    # detector (one-warp kernel + staged-id scan) and the persistent Almeida grid
+    ent = whole[0]
+    got, exp = ctx.detect_block_motion(ent), oracle.detect_block_motion(ent)
+    assert got[:3] == tuple(exp[:3]) and got[3].tobytes() == exp[3].tobytes()
+    fld, q_truth = synth.rotation_field(64, 36, 16 / 9, 22.275, (0.3, -0.2, 0.1))
+    q = ctx.almeida(fld, 16 / 9, 22.275)
+    q64 = oracle.almeida_lsq_f64(fld, 16 / 9, 22.275)
+    assert min(np.abs(q - q64).max(), np.abs(q + q64).max()) < 1e-4
+    checks += 2
+    print(f"sanitize_k1: {checks} checks passed")
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
