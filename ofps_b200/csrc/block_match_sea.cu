@@ -216,6 +216,12 @@ struct SeaOut {
     // peer-halo mode (spatial tiling over GPUs): the previous-frame tensor holds this rank's own rows only; the halo
     // rows above / below are read straight from the neighbours' HBM (tensor maps on peer-mapped memory)
     int peer, own_rows, up_rows, has_up, has_down;
+    // profiling hook (env OFPSB_DEBUG_SEA_STOP, tools/debug_sea_stop.py): 1 = return after the loads, 2 = after the window
+    // sums, 3 = after the tile predictor.  Measured on B200, us per 1080p pair: 1.62 / 1.88 / 2.26 of the kernel's 5.36 —
+    // the loads are bound by the TMA unit's row rate (u8 and u32 tensor descriptions take the same time; a direct copy by
+    // all threads with cp.async is faster alone, 1.25, but slows the whole kernel, 5.72: it takes issue slots from the CTAs
+    // that are computing, the TMA box does not)
+    int debug_stop;
 };
 
 // The current tile is staged as [16-byte column block][row][16 bytes] (transposing tensor map, tma_common.cuh): the rows of
@@ -633,12 +639,14 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
     }
     __syncthreads();
 #endif
+    if (out.debug_stop == 1) return;
     sea_hpass<C::N, C::PW, C::PH, C::SP>(sP, sS32, tid);
     sea_cur_sums<C, B>(sC, s_csum, tid);
     __syncthreads();
     sea_vpass<C>(sS32, tid);
     __syncthreads();
 
+    if (out.debug_stop == 2) return;
     // the whole tile is interior when no candidate of any of its blocks leaves the frame (CTA-uniform)
     const bool interior = tx0 - R >= 0 && tx0 + SEA_TILE_W + R <= p.w && ty0 - R >= -p.halo_top &&
                           ty0 + TH + R <= p.strip_h + p.halo_bottom &&
@@ -673,6 +681,7 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
         const int idx = (int)(kb & 4095u), dyi = idx / C::ND;
         pred = sea_pos(idx - dyi * C::ND - R, dyi - R, R);
     }
+    if (out.debug_stop == 3) return;
     // the warp's blocks; lane `it` keeps the result of block `it` and writes it after the loop (one pass of the output
     // code per warp instead of one per block)
     constexpr int NBW = C::TBY * C::CPW;
@@ -794,6 +803,7 @@ int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int
     out.nx = 1.0f / (float)p.w;          // av-decoder/src/lib.rs:404-405 (host code is built with -ffp-contract=off)
     out.ny = 1.0f / (float)p.full_h;
     out.prefetch_tiles = sc.prefetch_tiles >= 0 ? sc.prefetch_tiles : 3 * (sm_count > 0 ? sm_count : 148);
+    out.debug_stop = getenv("OFPSB_DEBUG_SEA_STOP") ? atoi(getenv("OFPSB_DEBUG_SEA_STOP")) : 0;
     out.peer = peer ? 1 : 0;
     out.own_rows = peer ? peer->own_rows : 0;
     out.up_rows = peer ? peer->up_rows : 0;

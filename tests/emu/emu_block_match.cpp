@@ -34,7 +34,7 @@ int emu_block_match_sea(const uint8_t* prev, const uint8_t* cur, int w, int stri
     p.mv_xy = mv; p.cost = cost; p.entries = entries;
     SeaOut out;
     out.worklist = worklist; out.wl_count = wl_count; out.stats = stats;
-    out.nx = 1.0f / (float)w; out.ny = 1.0f / (float)full_h; out.prefetch_tiles = 0;
+    out.nx = 1.0f / (float)w; out.ny = 1.0f / (float)full_h; out.prefetch_tiles = 0; out.debug_stop = 0;
     *wl_count = 0;
     const int th = tile_h == 32 ? 32 : 64;
     const dim3 grid((p.nbx * block + SEA_TILE_W - 1) / SEA_TILE_W, (p.nby * block + th - 1) / th, n_pairs);
