@@ -200,8 +200,6 @@ def run_ours(args):
     dev = f"cuda:{local_rank}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # "NCCL version ..." goes to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -369,6 +367,11 @@ def run_ours(args):
     if world > 1:
         extra["strong_c5"] = strong_c5(ctx, torch, dist, stream, flush, rank, world, dev, barrier, rank_max, args)
         extra["tiled_8k"] = tiled_8k(ctx, torch, dist, stream, flush, rank, world, dev, barrier, rank_max)
+        extra["tiled_c4"] = tiled_8k(ctx, torch, dist, stream, flush, rank, world, dev, barrier, rank_max, w=3840, h=2160, BLOCK=8,
+                                     SEARCH=32, n_stream=8,
+                                     label=f"BASELINE config 4: ONE 3840x2160 pair, 8x8/+-32 SAD, {world} strips; +-32 has no SEA "
+                                           "instance: round-1 pruning pipeline per strip, halo rows copied from the neighbours' "
+                                           "HBM by a kernel (peer pointers), no NCCL")
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = _peaks()
@@ -506,13 +509,15 @@ def strong_c5(ctx, torch, dist, stream, flush, rank, world, dev, barrier, rank_m
             "bit_equal_to_single_gpu": okf, "timing": "device events per rank, L2 flushed, max over ranks, median of steps"}
 
 
-def tiled_8k(ctx, torch, dist, stream, flush, rank, world, dev, barrier, rank_max):
+def tiled_8k(ctx, torch, dist, stream, flush, rank, world, dev, barrier, rank_max, w=7680, h=4320, BLOCK=BLOCK, SEARCH=SEARCH,
+             n_stream=None, label=None):
     """North-star geometry: ONE 7680x4320 pair, 16x16/+-16, cut into N strips; halo rows are read from the neighbours'
     HBM inside the kernel (ofpsb_tiled_*, CUDA IPC + NVLink), no exchange step.  Also a stream of tiled frames in one
-    launch sequence.  Bit-equality against the whole frame matched on each rank's own GPU comes first."""
+    launch sequence.  Bit-equality against the whole frame matched on each rank's own GPU comes first.
+    (Also used for BASELINE config 4: 3840x2160, 8x8/+-32.)"""
     from ofps_b200 import capi, synth
     from ofps_b200 import dist as odist
-    w, h, n_stream = 7680, 4320, TILED_STREAM_PAIRS
+    n_stream = TILED_STREAM_PAIRS if n_stream is None else n_stream
     frames = synth.make_stream(n_stream + 1, w, h, SEARCH, first_index=2000)
     m = odist.PeerTiledMatcher(ctx, w, h, BLOCK, SEARCH, rank, world, n_slots=n_stream + 1)
     t = m.t
@@ -560,8 +565,8 @@ def tiled_8k(ctx, torch, dist, stream, flush, rank, world, dev, barrier, rank_ma
         solo.close()
     okf = rank_max(0.0 if (ok and gathered_ok) else 1.0)[0] == 0.0
     m.close()
-    return {"workload": f"ONE 7680x4320 pair, 16x16/+-16 SAD, {world} strips of whole block rows; halo rows read from the "
-                        "neighbours' HBM inside the SEA kernel (peer-mapped tensor maps), no exchange step",
+    return {"workload": label or f"ONE 7680x4320 pair, 16x16/+-16 SAD, {world} strips of whole block rows; halo rows read from the "
+                                 "neighbours' HBM inside the SEA kernel (peer-mapped tensor maps), no exchange step",
             "pair_us": pair_us, "pair_one_gpu_us": one_pair_us, "pair_speedup_vs_1gpu": one_pair_us / pair_us,
             "pair_value": w * h / pair_us, "stream_pairs": n_stream, "stream_us": stream_us, "stream_one_gpu_us": one_stream_us,
             "stream_speedup_vs_1gpu": one_stream_us / stream_us, "stream_value": w * h * n_stream / stream_us, "unit": "Mpix/s",
@@ -583,6 +588,12 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--impl", args.impl]
         return subprocess.call(cmd)
+    # stdout carries exactly one JSON line: everything else written to fd 1 while the job runs (NCCL prints its
+    # version banner there from C, whatever NCCL_DEBUG says) is sent to stderr, the line goes to the saved descriptor
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 

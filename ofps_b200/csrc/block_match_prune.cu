@@ -463,12 +463,10 @@ static int pruned_chunk(const BlockMatchParams& p, BlockMatchScratch& sc, int sm
 int launch_block_match_pruned(const BlockMatchParams& p, BlockMatchScratch& sc, int sm_count, cudaStream_t stream,
                               uint64_t* launches)
 {
-    // the fused four-term SEA kernel covers every tuned geometry up to +-16; +-32 keeps the round-1 pipeline
-    if (sc.pruner != 1) {
-        const int rc = launch_block_match_sea(p, sc, sm_count, stream, launches);
-        if (rc != 1) return rc;
-    }
-    if (p.range < 32 && sc.pruner != 1) return 1;
+    // the fused four-term SEA kernel covers every tuned geometry; what it declines (or skips on content feedback) goes
+    // to the exhaustive kernels.  The round-1 pipeline below runs only on request ("block_match_pruner" = 1): at
+    // +-32 it is slower than the exhaustive search on all but noise-free 16x16 content.
+    if (sc.pruner != 1) return launch_block_match_sea(p, sc, sm_count, stream, launches);
     int chunk = sc.chunk_pairs;
     if (chunk <= 0) chunk = p.n_pairs;
     if (chunk >= p.n_pairs) return pruned_chunk(p, sc, sm_count, stream, launches, true);

@@ -77,7 +77,7 @@ struct SeaCfg {
     static constexpr int NEX = EXTRA ? (ND + 31) / 32 : 0;
     static constexpr int CPW = TBX / SEA_WARPS;           // block columns per warp
     static_assert(B == 8 || B == 16, "sub-block sums are staged for 8x8 and 16x16 blocks");
-    static_assert(ND <= 33, "bounds of one dx column group live in registers");
+    static_assert(ND <= 65, "lanes <-> dx in groups of 32 columns plus the dx = +R column; 7-bit position fields");
     static_assert(TBX % SEA_WARPS == 0 && PW % 16 == 0 && PW <= 256 && PH <= 256, "tile / TMA box limits");
     static_assert(SR >= N && NSEG >= 1, "vertical pass: a segment is at least one window high");
     static_assert(RA + B - R >= 2 * N, "every window-sum column a candidate reads is a full window");
@@ -290,6 +290,58 @@ struct SeaResult {   // per-block result, kept by lane `it` of the warp until th
     uint32_t cost, pos;
     bool resolved;
 };
+
+// Survivors of a full scan (s_list[0 .. total), total <= 32, entries dyi << 7 | dxi): one entry per lane — its bound and
+// position stay in registers — and the warp evaluates them in ascending bound order, re-testing every survivor against
+// the tightening best: entries that no longer qualify cost nothing.  skip*: positions already evaluated.
+template <int B, int R, int N, int PW, int SP>
+__device__ __forceinline__ void sea_eval_list(const uint32_t* __restrict__ s_list, int total, const uint16_t* __restrict__ s_blk,
+                                              const uint8_t* __restrict__ sP, int wx0, int wy0, uint32_t c0, uint32_t c1, int lane,
+                                              uint32_t C00, uint32_t C10, uint32_t C01, uint32_t C11, uint32_t skip0, uint32_t skip1,
+                                              uint32_t skip2, uint32_t& bc, uint32_t& bp, unsigned long long& evaluated)
+{
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    uint32_t lb = NONE, pos = NONE;
+    if (lane < total) {
+        const uint32_t e = s_list[lane];
+        const int dxi = (int)(e & 127u), dyi = (int)(e >> 7);
+        pos = sea_pos(dxi - R, dyi - R, R);
+        const uint16_t* q = s_blk + dyi * SP + dxi;   // s_blk: window sum of the block at (dx, dy) = (-R, -R)
+        lb = __usad(q[N * SP + N], C11, __usad(q[N * SP], C01, __usad(q[N], C10, __usad(q[0], C00, 0u))));
+        if (pos == skip0 || pos == skip1 || pos == skip2) lb = NONE;
+    }
+    for (;;) {
+        const bool cand = lb < bc || (lb == bc && pos < bp);
+        const uint32_t k = __reduce_min_sync(0xffffffffu, cand ? lb : NONE);
+        if (k == NONE) break;
+        const int l = __ffs(__ballot_sync(0xffffffffu, cand && lb == k)) - 1;
+        const uint32_t cp = __shfl_sync(0xffffffffu, pos, l);
+        const uint32_t c = sea_exact<B, PW>(sP, wx0 + (int)(cp & 127u) - R, wy0 + (int)((cp >> 7) & 127u) - R, c0, c1, lane);
+        evaluated++;
+        if (c < bc || (c == bc && cp < bp)) { bc = c; bp = cp; }
+        if (lane == l) lb = NONE;
+    }
+}
+
+// One chunk of RS rows of a +-32 full scan (sea_block_wide): row j of the chunk finishes the bound of dy index dyi0 + j
+// (started N rows earlier, ring slot j) and starts the bound whose upper sub-blocks it holds (slot (j + N) % RS).
+// kc: smallest bound << 7 | j of the chunk; code: bit j set when the bound is not above `thr`.  CHECK: the chunk
+// holds rows outside the legal dy range (j - lo_rel > span, unsigned).
+template <int N, int SP, int RS, bool CHECK>
+__device__ __forceinline__ void sea_scan_chunk(const uint16_t* __restrict__ q, uint32_t (&acc)[RS], uint32_t C00, uint32_t C10,
+                                               uint32_t C01, uint32_t C11, uint32_t thr, int lo_rel, uint32_t span, uint32_t& kc,
+                                               uint32_t& code)
+{
+#pragma unroll
+    for (int j = 0; j < RS; j++) {
+        const uint32_t sa = q[j * SP], sb = q[j * SP + N];
+        uint32_t b = __usad(sb, C11, __usad(sa, C01, acc[j]));
+        if (CHECK && (uint32_t)(j - lo_rel) > span) b = SEA_BIG;
+        kc = min(kc, b * 128u + (uint32_t)j);
+        code |= (b <= thr ? 1u : 0u) << j;
+        acc[(j + N) % RS] = __usad(sb, C10, __usad(sa, C00, 0u));
+    }
+}
 
 // ---- step 3: one block, one warp ------------------------------------------------------------------------------------
 // sS: window sums (u16, pitch PW), sP: previous-frame window, sC: current tile.  (bxl, byl): block inside the tile.
@@ -524,21 +576,253 @@ __device__ __forceinline__ SeaResult sea_block(const uint16_t* __restrict__ sS, 
                 while (mhi) { const int dyi = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; s_list[slot++] = ((uint32_t)dyi << 7) | (uint32_t)lane; }
                 while (mex) { const int t = __ffs(mex) - 1; mex &= mex - 1; s_list[slot++] = ((uint32_t)(lane + 32 * t) << 7) | (uint32_t)(2 * R); }
                 __syncwarp();
-                for (int i = 0; i < total; i++) {
-                    const uint32_t e = s_list[i];
-                    const int dxi = (int)(e & 127u), dyi = (int)(e >> 7);
-                    const uint32_t pos = sea_pos(dxi - R, dyi - R, R);
-                    if (pos == zpos || pos == pred || pos == pos_min) continue;   // already evaluated
-                    if (bc == 0 && pos > bp) continue;
-                    const uint16_t* q = sS + (byl * B + dyi) * SP + wx0 - R + dxi;
-                    const uint32_t lb = __usad(q[N * SP + N], C11, __usad(q[N * SP], C01, __usad(q[N], C10, __usad(q[0], C00, 0u))));
-                    if (!(lb < bc || (lb == bc && pos < bp))) continue;           // the best tightened meanwhile
-                    const uint32_t c = sea_exact<B, PW>(sP, wx0 + dxi - R, wy0 + dyi - R, c0, c1, lane);
-                    evaluated++;
-                    if (c < bc || (c == bc && pos < bp)) { bc = c; bp = pos; }
-                }
+                sea_eval_list<B, R, N, PW, SP>(s_list, total, sS + byl * B * SP + wx0 - R, sP, wx0, wy0, c0, c1, lane, C00, C10, C01, C11,
+                                               zpos, pred, pos_min, bc, bp, evaluated);
                 __syncwarp();
             }
+        }
+    }
+    if (out.stats && lane == 0) {
+        atomicAdd(&out.stats[0], 1ull);
+        atomicAdd(&out.stats[1], resolved ? 1ull : 0ull);
+        atomicAdd(&out.stats[2], evaluated);
+        atomicAdd(&out.stats[3], full_scan ? 1ull : 0ull);
+    }
+    SeaResult res;
+    res.cost = bc;
+    res.pos = bp;
+    res.resolved = resolved;
+    return res;
+}
+
+// ---- step 3 for +-32 (65 x 65 candidates): the lanes <-> dx mapping runs over two groups of 32 columns (dx = lane - R + 32 g)
+// plus the dx = +R column, and the bounds of a column no longer fit a warp's registers: the full scan makes two passes
+// with a rolling window of N + 1 accumulators (a bound is complete N rows after it was started) — pass 1 folds the
+// smallest (bound, position) key, pass 2 recomputes the bounds and collects the survivors.  Everything else is the
+// +-16 procedure above.
+template <int B, int R, int TH>
+__device__ __forceinline__ SeaResult sea_block_wide(const uint16_t* __restrict__ sS, const uint8_t* __restrict__ sP,
+                                                    const uint8_t* __restrict__ sC, const uint32_t* __restrict__ s_csum,
+                                                    const BlockMatchParams& p, int bx, int by, int bxl, int byl, bool interior,
+                                                    uint32_t pred, int lane, uint32_t* __restrict__ s_list, const SeaOut& out)
+{
+    using C = SeaCfg<B, R, TH>;
+    constexpr int N = C::N, ND = C::ND, PW = C::PW, SP = C::SP, NG = (ND - 1) / 32, NEX = C::NEX;
+    static_assert(ND == 65 && NG == 2, "two groups of 32 columns and the dx = +R column; 64 + 1 rows in the survivor masks");
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    int dy_lo = -R, dy_hi = R, dx_lo = -R, dx_hi = R;
+    if (!interior) {
+        const int x0 = bx * B, y0 = by * B;
+        dy_lo = max(-R, -p.halo_top - y0);
+        dy_hi = min(R, p.strip_h + p.halo_bottom - B - y0);
+        dx_lo = max(-R, -x0);
+        dx_hi = min(R, p.w - B - x0);
+    }
+    const int wx0 = bxl * B + C::RA, wy0 = byl * B + R;
+    uint32_t c0, c1;
+    sea_cur_block<B, C::CH>(sC, bxl, byl, lane, c0, c1);
+    const uint4 csum = *reinterpret_cast<const uint4*>(s_csum + 4 * (byl * C::TBX + bxl));
+    const uint32_t C00 = csum.x, C10 = csum.y, C01 = csum.z, C11 = csum.w;
+
+    const uint32_t pos00 = sea_pos(0, 0, R);
+    int pdx = (int)(pred & 127u) - R, pdy = (int)((pred >> 7) & 127u) - R;
+    if (!interior && (pdx < dx_lo || pdx > dx_hi || pdy < dy_lo || pdy > dy_hi)) {
+        pred = pos00;
+        pdx = pdy = 0;
+    }
+    uint32_t bc = sea_exact<B, PW>(sP, wx0 + pdx, wy0 + pdy, c0, c1, lane);
+    uint32_t bp = pred;
+    unsigned long long evaluated = 1;
+    uint32_t zpos = pred == pos00 ? pos00 : NONE;
+    if (bc != 0 && pred != pos00) {
+        const uint32_t c = sea_exact<B, PW>(sP, wx0, wy0, c0, c1, lane);
+        evaluated++;
+        zpos = pos00;
+        if (c < bc || (c == bc && pos00 < bp)) { bc = c; bp = pos00; }
+    }
+    const uint16_t* scol0 = sS + byl * B * SP + wx0 - R + lane;   // window sum at (dx = lane - R, dy = -R); group g: + 32 g
+    bool resolved = true, full_scan = false;
+
+    if (bc == 0) {
+        if (bp != pos00) {
+            const int d2 = (int)(bp >> 14);
+            const int bdx = pdx, bdy = pdy;
+            int r = max(abs(bdx), abs(bdy));
+            while ((r + 1) * (r + 1) <= d2) r++;
+            const int ya = max(-r, dy_lo), yb = min(r, dy_hi);
+            constexpr int G = N >= 8 ? 8 : 4;
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                if (32 * g - R > r || 32 * g - R + 31 < -r) continue;   // the group holds no column of the disc (warp-uniform)
+                const int dx = lane - R + 32 * g;
+                const uint32_t c00l = dx >= dx_lo && dx <= dx_hi && dx != bdx ? C00 : NONE;
+                const uint16_t* qg = scol0 + 32 * g + (ya + R) * SP;
+                for (int dyq = ya; dyq <= yb; dyq += G, qg += G * SP) {
+                    bool any = false;
+#pragma unroll
+                    for (int j = 0; j < G; j++) any |= (uint32_t)qg[j * SP] == c00l;
+                    if (__ballot_sync(0xffffffffu, any) == 0u) continue;
+                    uint32_t code = 0;
+#pragma unroll
+                    for (int j = 0; j < G; j++) code |= ((uint32_t)qg[j * SP] == c00l ? 1u : 0u) << j;
+                    const int nrow = yb - dyq + 1;
+                    if (nrow < G) code &= (1u << nrow) - 1u;
+                    unsigned rows = __reduce_or_sync(0xffffffffu, code);
+                    while (rows) {
+                        const int j = __ffs(rows) - 1;
+                        rows &= rows - 1;
+                        const int dy = dyq + j;
+                        const uint16_t* q = qg + j * SP;
+                        const uint32_t pos = sea_pos(dx, dy, R);
+                        const bool zero = ((code >> j) & 1u) && pos < bp && (uint32_t)q[N] == C10 && (uint32_t)q[N * SP] == C01 &&
+                                          (uint32_t)q[N * SP + N] == C11;
+                        unsigned m = __ballot_sync(0xffffffffu, zero);
+                        while (m) {
+                            const int l = __ffs(m) - 1;
+                            m &= m - 1;
+                            const uint32_t cp = __shfl_sync(0xffffffffu, pos, l);
+                            if (cp >= bp) continue;
+                            const uint32_t c = sea_exact<B, PW>(sP, wx0 + l - R + 32 * g, wy0 + dy, c0, c1, lane);
+                            evaluated++;
+                            if (c == 0) bp = cp;
+                        }
+                    }
+                }
+            }
+            // the best's own column, and the dx = +R column when the disc reaches it: lanes <-> dy
+#pragma unroll
+            for (int which = 0; which < 2; which++) {
+                const int cdx = which == 0 ? bdx : R;
+                if (which == 1 && (R * R > d2 || R > dx_hi || bdx == R)) continue;
+                const uint16_t* col = sS + (byl * B + R) * SP + wx0 + cdx;
+#pragma unroll
+                for (int t = 0; t < NEX; t++) {
+                    if (t > 0 && ya + 32 * t > yb) break;
+                    const int dy = ya + lane + 32 * t;
+                    const uint16_t* q = col + min(dy, yb) * SP;
+                    const uint32_t pos = sea_pos(cdx, dy, R);
+                    const bool hit = dy <= yb && !(cdx == bdx && dy == bdy) && (uint32_t)q[0] == C00;
+                    if (__ballot_sync(0xffffffffu, hit) == 0u) continue;
+                    const bool zero = hit && pos < bp && (uint32_t)q[N] == C10 && (uint32_t)q[N * SP] == C01 &&
+                                      (uint32_t)q[N * SP + N] == C11;
+                    unsigned m = __ballot_sync(0xffffffffu, zero);
+                    while (m) {
+                        const int l = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t cp = __shfl_sync(0xffffffffu, pos, l);
+                        if (cp >= bp) continue;
+                        const uint32_t c = sea_exact<B, PW>(sP, wx0 + cdx, wy0 + ya + l + 32 * t, c0, c1, lane);
+                        evaluated++;
+                        if (c == 0) bp = cp;
+                    }
+                }
+            }
+        }
+    } else {
+        full_scan = true;
+        // ---- pass 1: per column, the smallest bound (key bound << 7 | dy index) and the candidates whose bound is not
+        // above the cost of the best so far.  RS rows per trip of a rolled loop (unrolled, the loads are hoisted and the
+        // ring of accumulators spills); a trip whose rows are all legal skips the range test.
+        constexpr int RS = N + 1 <= 5 ? 5 : 13;   // ring slots: a divisor of ND not below N + 1
+        static_assert(ND % RS == 0 && RS >= N + 1 && RS <= 32, "whole trips, one code bit per row");
+        const uint16_t* s_blk = scol0 - lane;
+        uint32_t bex[NEX];
+        uint32_t my_lb = SEA_BIG, my_pos = NONE;
+#pragma unroll
+        for (int t = 0; t < NEX; t++) {
+            const int dyi = lane + 32 * t, dy = dyi - R;
+            const bool ok = dyi < ND && dy >= dy_lo && dy <= dy_hi && R <= dx_hi;
+            const uint16_t* q = s_blk + (dyi < ND ? dyi : 0) * SP + 2 * R;
+            const uint32_t v = __usad(q[N * SP + N], C11, __usad(q[N * SP], C01, __usad(q[N], C10, __usad(q[0], C00, 0u))));
+            bex[t] = ok ? v : SEA_BIG;
+            const uint32_t pos = sea_pos(R, dy, R);
+            if (bex[t] < my_lb || (bex[t] == my_lb && bex[t] < SEA_BIG && pos < my_pos)) { my_lb = bex[t]; my_pos = pos; }
+        }
+        const int lo_i = dy_lo + R;
+        const uint32_t span = (uint32_t)(dy_hi - dy_lo);
+        uint32_t pos_min = NONE;
+        int total = 0;
+        unsigned long long msk[NG];   // bit dyi of the group's column; the last row (dyi = 2 R) in top
+        uint32_t top = 0, mex = 0;
+        int mine = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            mine = 0;
+            top = 0;
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                const int dx = lane - R + 32 * g;
+                const bool lin = dx >= dx_lo && dx <= dx_hi;
+                const uint16_t* q = scol0 + 32 * g;
+                uint32_t acc[RS], kmin = NONE, code = 0;
+                unsigned long long mk = 0;
+#pragma unroll
+                for (int t = 0; t < N; t++) acc[t] = __usad(q[t * SP + N], C10, __usad(q[t * SP], C00, 0u));
+                q += N * SP;
+#pragma unroll 1
+                for (int d0 = 0; d0 < ND; d0 += RS, q += RS * SP) {
+                    uint32_t kc = NONE;
+                    code = 0;
+                    if (interior || (d0 >= lo_i && d0 + RS - 1 <= lo_i + (int)span))
+                        sea_scan_chunk<N, SP, RS, false>(q, acc, C00, C10, C01, C11, bc, 0, 0u, kc, code);
+                    else
+                        sea_scan_chunk<N, SP, RS, true>(q, acc, C00, C10, C01, C11, bc, lo_i - d0, span, kc, code);
+                    kmin = min(kmin, kc + (uint32_t)d0);
+                    mk |= (unsigned long long)code << d0;
+                }
+                if (lin) {
+                    msk[g] = mk;
+                    top |= ((code >> (RS - 1)) & 1u) << g;   // the last trip's last row: dy index 2 R
+                    if ((kmin >> 7) < SEA_BIG) {
+                        const uint32_t lb = kmin >> 7, pos = sea_pos(dx, (int)(kmin & 127u) - R, R);
+                        if (lb < my_lb || (lb == my_lb && pos < my_pos)) { my_lb = lb; my_pos = pos; }
+                    }
+                } else {
+                    msk[g] = 0;
+                }
+                mine += __popcll(msk[g]) + (int)((top >> g) & 1u);
+            }
+            mex = 0;
+#pragma unroll
+            for (int t = 0; t < NEX; t++)
+                if (bex[t] <= bc) mex |= 1u << t;
+            mine += __popc(mex);
+            total = (int)__reduce_add_sync(0xffffffffu, (uint32_t)mine);
+            if (total <= SEA_CAP || pass == 1) break;
+            // too many survivors under the predictor's cost: evaluate the candidate of the smallest bound and count again
+            const uint32_t lb_min = __reduce_min_sync(0xffffffffu, my_lb);
+            pos_min = __reduce_min_sync(0xffffffffu, my_lb == lb_min ? my_pos : NONE);
+            if (lb_min > bc || pos_min == zpos || pos_min == pred) break;
+            const uint32_t c = sea_exact<B, PW>(sP, wx0 + (int)(pos_min & 127u) - R, wy0 + (int)((pos_min >> 7) & 127u) - R, c0, c1, lane);
+            evaluated++;
+            if (c < bc || (c == bc && pos_min < bp)) { bc = c; bp = pos_min; }
+            else break;   // nothing tightened: the count stands
+        }
+        if (total > SEA_CAP) {
+            resolved = false;
+        } else if (total > 0) {
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = (int)__shfl_up_sync(0xffffffffu, (uint32_t)incl, o);
+                if (lane >= o) incl += u;
+            }
+            int slot = incl - mine;
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                unsigned long long m = msk[g];
+                while (m) {
+                    const int dyi = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    s_list[slot++] = ((uint32_t)dyi << 7) | (uint32_t)(lane + 32 * g);
+                }
+                if ((top >> g) & 1u) s_list[slot++] = ((uint32_t)(2 * R) << 7) | (uint32_t)(lane + 32 * g);
+            }
+            while (mex) { const int t = __ffs(mex) - 1; mex &= mex - 1; s_list[slot++] = ((uint32_t)(lane + 32 * t) << 7) | (uint32_t)(2 * R); }
+            __syncwarp();
+            sea_eval_list<B, R, N, PW, SP>(s_list, total, s_blk, sP, wx0, wy0, c0, c1, lane, C00, C10, C01, C11, zpos, pred, pos_min, bc, bp,
+                                           evaluated);
+            __syncwarp();
         }
     }
     if (out.stats && lane == 0) {
@@ -667,7 +951,7 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
             const uint16_t* q = sS + dyi * SP + C::RA - R + dxi;
             const uint32_t v = __usad(q[N * SP + N], cs.w, __usad(q[N * SP], cs.z, __usad(q[N], cs.y, __usad(q[0], cs.x, 0u))));
             const bool ok = interior || (dxi - R >= dx_lo && dxi - R <= dx_hi && dyi - R >= dy_lo && dyi - R <= dy_hi);
-            if (ok) kb = min(kb, (v << 12) | (uint32_t)idx);
+            if (ok) kb = min(kb, (v << 13) | (uint32_t)idx);   // v < 2^16, idx < 65 * 65 < 2^13
         }
         kb = __reduce_min_sync(0xffffffffu, kb);
         if (lane == 0) s_probe[warp] = kb;
@@ -678,7 +962,7 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
         uint32_t kb = s_probe[0];
 #pragma unroll
         for (int i = 1; i < SEA_WARPS; i++) kb = min(kb, s_probe[i]);
-        const int idx = (int)(kb & 4095u), dyi = idx / C::ND;
+        const int idx = (int)(kb & 8191u), dyi = idx / C::ND;
         pred = sea_pos(idx - dyi * C::ND - R, dyi - R, R);
     }
     if (out.debug_stop == 3) return;
@@ -692,7 +976,9 @@ __global__ void __launch_bounds__(SEA_NT, 3) sea_kernel(const __grid_constant__ 
         const int byl = it / C::CPW, bxl = warp * C::CPW + it % C::CPW;
         const int bx = tx0 / B + bxl, by = ty0 / B + byl;
         if (bx >= p.nbx || by >= p.nby) continue;
-        const SeaResult res = sea_block<B, R, TH>(sS, sP, sC, s_csum, p, bx, by, bxl, byl, interior, pred, lane, s_list[warp], out);
+        SeaResult res;
+        if constexpr (C::ND > 33) res = sea_block_wide<B, R, TH>(sS, sP, sC, s_csum, p, bx, by, bxl, byl, interior, pred, lane, s_list[warp], out);
+        else res = sea_block<B, R, TH>(sS, sP, sC, s_csum, p, bx, by, bxl, byl, interior, pred, lane, s_list[warp], out);
         pred = res.pos;
         if (lane == it) {
             r_cost = res.cost;
@@ -755,7 +1041,9 @@ int launch_sea(const BlockMatchParams& p, const SeaOut& out, const SeaPeer* peer
 {
     const long long tiles64 = (long long)((p.nbx * B + SEA_TILE_W - 1) / SEA_TILE_W) * ((p.nby * B + 63) / 64) * p.n_pairs;
     const bool small = tile_h == 32 || (tile_h == 0 && tiles64 <= 6ll * (sm_count > 0 ? sm_count : 148));
-    return small ? launch_sea_th<B, R, 32>(p, out, peer, stream) : launch_sea_th<B, R, 64>(p, out, peer, stream);
+    if constexpr (R > 16)   // +-32: 64-row tiles leave two CTAs per SM (measured: 4K 8x8 176 vs 149 us per pair, 1080p 16x16 equal)
+        return launch_sea_th<B, R, 32>(p, out, peer, stream);
+    else return small ? launch_sea_th<B, R, 32>(p, out, peer, stream) : launch_sea_th<B, R, 64>(p, out, peer, stream);
 }
 #endif
 
@@ -772,7 +1060,7 @@ int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int
                            uint64_t* launches, const SeaPeer* peer, cudaEvent_t before_list)
 {
     if (p.metric != OFPSB_METRIC_SAD || !block_match_tma_usable(p)) return 1;
-    const bool geom = (p.block == 16 || p.block == 8) && (p.range == 8 || p.range == 16);
+    const bool geom = (p.block == 16 || p.block == 8) && (p.range == 8 || p.range == 16 || p.range == 32);
     if (!geom) return 1;
     const int rows_prev = p.halo_top + p.strip_h + p.halo_bottom;
     if (p.w < p.block || rows_prev < p.block) return 1;
@@ -784,7 +1072,8 @@ int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int
     // content feedback from the previous SEA launch (never blocks: an unfinished read-back is simply not used yet)
     if (sc.adaptive && !peer && !sc.collect_stats) {
         if (sc.ev_listed && sc.listed_total > 0 && cudaEventQuery(sc.ev_listed) == cudaSuccess) {
-            if ((double)sc.h_listed[0] > 0.6 * (double)sc.listed_total) sc.skip_calls = 15;
+            // the +-32 kernel costs a larger share of the exhaustive search it replaces (4K 8x8: 0.5-0.8 on noisy content)
+            if ((double)sc.h_listed[0] > (p.range > 16 ? 0.3 : 0.6) * (double)sc.listed_total) sc.skip_calls = 15;
             sc.listed_total = 0;
         }
         cudaGetLastError();
@@ -818,6 +1107,8 @@ int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int
     else if (p.block == 16 && p.range == 8) rc = launch_sea<16, 8>(p, out, peer, stream, sm_count, sc.tile_h);
     else if (p.block == 8 && p.range == 16) rc = launch_sea<8, 16>(p, out, peer, stream, sm_count, sc.tile_h);
     else if (p.block == 8 && p.range == 8) rc = launch_sea<8, 8>(p, out, peer, stream, sm_count, sc.tile_h);
+    else if (p.block == 8 && p.range == 32) rc = launch_sea<8, 32>(p, out, peer, stream, sm_count, sc.tile_h);
+    else if (p.block == 16 && p.range == 32) rc = launch_sea<16, 32>(p, out, peer, stream, sm_count, sc.tile_h);
     if (rc) return rc;
     if (sc.profile && sc.ev[1]) OFPSB_CUDA_TRY(cudaEventRecord(sc.ev[1], stream));
     // the exhaustive kernel reads halo rows stored with the strip: in peer-halo mode they are copied on a side

@@ -36,7 +36,7 @@ int emu_block_match_sea(const uint8_t* prev, const uint8_t* cur, int w, int stri
     out.worklist = worklist; out.wl_count = wl_count; out.stats = stats;
     out.nx = 1.0f / (float)w; out.ny = 1.0f / (float)full_h; out.prefetch_tiles = 0; out.debug_stop = 0;
     *wl_count = 0;
-    const int th = tile_h == 32 ? 32 : 64;
+    const int th = (tile_h == 32 || range > 16) ? 32 : 64;
     const dim3 grid((p.nbx * block + SEA_TILE_W - 1) / SEA_TILE_W, (p.nby * block + th - 1) / th, n_pairs);
     SeaMaps maps{};
 #define EMU_SEA(BB, RR)                                                                                   \
@@ -48,6 +48,8 @@ int emu_block_match_sea(const uint8_t* prev, const uint8_t* cur, int w, int stri
     else if (block == 16 && range == 8) EMU_SEA(16, 8);
     else if (block == 8 && range == 16) EMU_SEA(8, 16);
     else if (block == 8 && range == 8) EMU_SEA(8, 8);
+    else if (block == 8 && range == 32) OFPSB_LAUNCH_SMEM((sea_kernel<8, 32, 32>), grid, SEA_NT, 0, nullptr, maps, p, out);
+    else if (block == 16 && range == 32) OFPSB_LAUNCH_SMEM((sea_kernel<16, 32, 32>), grid, SEA_NT, 0, nullptr, maps, p, out);
 #undef EMU_SEA
     else return 1;
     return 0;

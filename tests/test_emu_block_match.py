@@ -99,6 +99,31 @@ def test_sea_half_height_tiles(emu, oracle, block, search, w, h, noise):
     check(emu, oracle, prev, cur, block, search, min_resolved=0.5, tile_h=32)
 
 
+@pytest.mark.parametrize("block,search,w,h,noise", [
+    (8, 32, 328, 136, 0), (8, 32, 328, 136, 2), (16, 32, 384, 208, 0), (16, 32, 400, 176, 3), (8, 32, 136, 72, 1),
+])
+def test_sea_wide_range(emu, oracle, block, search, w, h, noise):
+    """+-32 (BASELINE config 4): two groups of 32 dx columns plus the dx = +32 column, two-pass full scan."""
+    prev, cur, _ = synth.make_pair(w, h, search, index=9, noise_lsb=noise)
+    frac, stats = check(emu, oracle, prev, cur, block, search, min_resolved=0.4)
+    print(f"b{block} r{search} {w}x{h} noise {noise}: resolved {frac:.3f}, exact evals/block {stats[2] / stats[0]:.2f}, "
+          f"full scans {stats[3] / stats[0]:.2f}")
+
+
+def test_sea_wide_range_ties_and_extremes(emu, oracle):
+    prev = ((np.arange(160)[:, None] % 6) * 40 + (np.arange(256)[None] % 5) * 9).astype(np.uint8)
+    check(emu, oracle, prev, np.roll(np.roll(prev, 2, axis=0), -4, axis=1), 8, 32)
+    check(emu, oracle, prev, np.roll(np.roll(prev, 2, axis=0), -4, axis=1), 16, 32)
+    check(emu, oracle, np.full((96, 160), 9, np.uint8), np.full((96, 160), 9, np.uint8), 8, 32, min_resolved=1.0)
+    a, b = synth.textured_plane(1, 256, 128), synth.textured_plane(2, 256, 128)
+    check(emu, oracle, a, b, 8, 32)
+    check(emu, oracle, a, np.roll(a, 40, axis=1), 16, 32)             # panned beyond the range
+    check(emu, oracle, a, np.roll(np.roll(a, 32, axis=1), -32, axis=0), 8, 32)   # exactly on the dx = +R column / dy = -R row
+    rng = np.random.default_rng(5)
+    hi = rng.integers(0, 2, (128, 256)).astype(np.uint8) * 255
+    check(emu, oracle, hi, 255 - hi, 16, 32)
+
+
 def test_sea_ties_and_flat(emu, oracle):
     prev = np.full((96, 160), 77, np.uint8)
     frac, _ = check(emu, oracle, prev, prev.copy(), 16, 16, min_resolved=1.0)

@@ -66,6 +66,21 @@ for noise in (0, 2, 6):
         res[name] = {"us_per_pair": 1e3 * t / PAIRS, "Gpix_s": W * H * PAIRS / t / 1e6, "bit_equal_to_exhaustive": same,
                      "stats": {k: int(v) for k, v in st.items()}}
     ctx.set_option("block_match_pruner", 0)
+    # SEA kernel / work-list kernel split (events around each inside the library) and the tile-height variants
+    for th in (0, 32, 64):
+        ctx.set_option("block_match_tile_h", th)
+        ctx.set_option("block_match_adaptive", 0)
+        t = timed()
+        ctx.set_option("block_match_profile", 1)
+        ks = []
+        for _ in range(3):
+            step(); ctx.sync()
+            ks.append(ctx.block_match_kernel_ms())
+        ctx.set_option("block_match_profile", 0)
+        res[f"tile_h_{th}"] = {"us_per_pair": 1e3 * t / PAIRS, "sea_kernel_us_per_pair": 1e3 * ks[-1][0] / PAIRS,
+                               "list_kernel_us_per_pair": 1e3 * ks[-1][1] / PAIRS}
+    ctx.set_option("block_match_tile_h", 0)
+    ctx.set_option("block_match_adaptive", 1)
     print(json.dumps(res), flush=True)
 
 # L2 prefetch distance of the SEA kernel (tiles ahead), noise-free stream
