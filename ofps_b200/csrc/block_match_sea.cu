@@ -650,7 +650,7 @@ __device__ __forceinline__ SeaResult sea_block_wide(const uint16_t* __restrict__
             int r = max(abs(bdx), abs(bdy));
             while ((r + 1) * (r + 1) <= d2) r++;
             const int ya = max(-r, dy_lo), yb = min(r, dy_hi);
-            constexpr int G = N >= 8 ? 8 : 4;
+            constexpr int G = 8;
 #pragma unroll
             for (int g = 0; g < NG; g++) {
                 if (32 * g - R > r || 32 * g - R + 31 < -r) continue;   // the group holds no column of the disc (warp-uniform)
