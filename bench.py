@@ -369,9 +369,8 @@ def run_ours(args):
         extra["tiled_8k"] = tiled_8k(ctx, torch, dist, stream, flush, rank, world, dev, barrier, rank_max)
         extra["tiled_c4"] = tiled_8k(ctx, torch, dist, stream, flush, rank, world, dev, barrier, rank_max, w=3840, h=2160, BLOCK=8,
                                      SEARCH=32, n_stream=8,
-                                     label=f"BASELINE config 4: ONE 3840x2160 pair, 8x8/+-32 SAD, {world} strips; +-32 has no SEA "
-                                           "instance: round-1 pruning pipeline per strip, halo rows copied from the neighbours' "
-                                           "HBM by a kernel (peer pointers), no NCCL")
+                                     label=f"BASELINE config 4: ONE 3840x2160 pair, 8x8/+-32 SAD, {world} strips; halo rows read from the "
+                                           "neighbours' HBM inside the +-32 SEA kernel (peer-mapped tensor maps), no exchange step")
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = _peaks()
