@@ -124,6 +124,18 @@ def test_sea_wide_range_ties_and_extremes(emu, oracle):
     check(emu, oracle, hi, 255 - hi, 16, 32)
 
 
+def test_sea_wide_range_strips(emu, oracle):
+    """+-32 strips with 32 halo rows of the previous frame (tiled frames): rows of the whole-frame result."""
+    prev, cur, _ = synth.make_pair(264, 224, 32, index=11, noise_lsb=1)
+    omv, ocost, _ = oracle.block_match(prev, cur, 8, 32, 0, threads=oracle.max_threads(), fast=True)
+    for y0, rows in ((0, 64), (64, 96), (160, 64)):
+        mv, cost, ent, res, _ = run_sea(emu, prev, cur, 8, 32, strip=(y0, rows))
+        sl = slice(y0 // 8, (y0 + rows) // 8)
+        r = res[0]
+        np.testing.assert_array_equal(cost[0][r], ocost[sl][r])
+        np.testing.assert_array_equal(mv[0][r], omv[sl][r])
+
+
 def test_sea_ties_and_flat(emu, oracle):
     prev = np.full((96, 160), 77, np.uint8)
     frac, _ = check(emu, oracle, prev, prev.copy(), 16, 16, min_resolved=1.0)

@@ -10,3 +10,7 @@ if [ "$1" != "quick" ]; then
   python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
   cut -c1-600 gpurun_out/bench_reference.json
 fi
+if [ "$2" = "sanitize" ]; then
+  timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_k1.py > gpurun_out/sanitize_memcheck.txt 2>&1; tail -3 gpurun_out/sanitize_memcheck.txt
+  timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_k1.py > gpurun_out/sanitize_racecheck.txt 2>&1; tail -3 gpurun_out/sanitize_racecheck.txt
+fi

@@ -20,7 +20,8 @@ def main():
     oracle.build()
     ctx = capi.Context(0)
     checks = 0
-    for (w, h, b, r, noise) in ((320, 144, 16, 16, 0), (336, 104, 16, 8, 1), (160, 72, 8, 16, 2), (168, 48, 8, 8, 0)):
+    for (w, h, b, r, noise) in ((320, 144, 16, 16, 0), (336, 104, 16, 8, 1), (160, 72, 8, 16, 2), (168, 48, 8, 8, 0),
+                                (264, 136, 8, 32, 1), (272, 144, 16, 32, 0)):
         prev, cur, _ = synth.make_pair(w, h, r, index=checks, noise_lsb=noise)
         mv, cost, ent = oracle.block_match(prev, cur, b, r, 0, threads=oracle.max_threads(), fast=True)
         for th in (64, 32):
@@ -52,6 +53,29 @@ def main():
         ctx.dev_free(de)
         parts.append(e)
     assert np.concatenate(parts, axis=1).tobytes() == whole.tobytes()
+    for t in ts:
+        t.close()
+    checks += 1
+    # +-32 strips (two ranks on one device): seam rows of the 192 x 96 window come from the neighbour
+    fr32 = synth.make_stream(2, 264, 208, 32, noise_lsb=1)
+    whole32 = ctx.block_match(fr32[0], fr32[1], 8, 32, 0, want=("entries",))["entries"].reshape(-1, 4)
+    ts = [capi.Tiled(ctx, k, 2, 264, 208, 8, 32, 2) for k in range(2)]
+    ts[0].connect_local(None, ts[1])
+    ts[1].connect_local(ts[0], None)
+    for t in ts:
+        for s_ in range(2):
+            t.upload(s_, fr32[s_, t.y0:t.y0 + t.own_rows])
+            t.publish(s_)
+    parts = []
+    for t in ts:
+        de = ctx.dev_alloc(t.n_blocks * 16)
+        t.match(0, 1, de)
+        ctx.sync()
+        e = np.empty((t.n_blocks, 4), np.float32)
+        ctx.to_host(e, de)
+        ctx.dev_free(de)
+        parts.append(e)
+    assert np.concatenate(parts, axis=0).tobytes() == whole32.tobytes()
     for t in ts:
         t.close()
     checks += 1
