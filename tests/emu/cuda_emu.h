@@ -130,6 +130,14 @@ inline uint32_t __reduce_or_sync(unsigned mask, uint32_t v)   // subgroup masks:
         if ((mask >> i) & 1u) s |= t[i];
     return s;
 }
+inline uint32_t __reduce_max_sync(unsigned, uint32_t v)
+{
+    uint32_t t[32], s = 0;
+    emu_exchange(v, t);
+    for (int i = 0; i < 32; i++) s = t[i] > s ? t[i] : s;
+    return s;
+}
+inline void __trap() { abort(); }
 inline uint32_t __reduce_min_sync(unsigned, uint32_t v)
 {
     uint32_t t[32], s = 0xffffffffu;
