@@ -171,7 +171,7 @@ def bind_to_gpu_numa(local_rank: int):
         with open(f"/sys/bus/pci/devices/{dev}/numa_node") as f:
             node = int(f.read().strip())
         if node < 0:
-            return {"numa_node": None}
+            return probe_numa(local_rank)
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             cpus = set()
             for part in f.read().strip().split(","):
@@ -183,6 +183,57 @@ def bind_to_gpu_numa(local_rank: int):
         return {"numa_node": node, "cpus": len(cpus)}
     except Exception as e:
         return {"numa_node": None, "note": type(e).__name__}
+
+
+def _node_cpus():
+    import glob
+    out = {}
+    for d in glob.glob("/sys/devices/system/node/node[0-9]*"):
+        cpus = set()
+        with open(os.path.join(d, "cpulist")) as f:
+            txt = f.read().strip()
+        for part in txt.split(",") if txt else []:
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            out[int(os.path.basename(d)[4:])] = cpus
+    return out
+
+
+def probe_numa(local_rank: int):
+    """sysfs does not know the GPU's NUMA node (virtualised PCI topology): when the host has several nodes, time a
+    pinned H2D copy first-touched from each of them and bind to the fastest — only if it is clearly (> 10 %) faster."""
+    nodes = _node_cpus()
+    if len(nodes) < 2:
+        return {"numa_node": None, "host_nodes": len(nodes)}
+    import torch
+    all_cpus = os.sched_getaffinity(0)
+    torch.cuda.set_device(local_rank)
+    dst = torch.empty(64 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    rates = {}
+    for n, cpus in sorted(nodes.items()):
+        os.sched_setaffinity(0, cpus)
+        src = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        src.fill_(1)                                           # first touch on this node
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        rates[n] = 4 * src.numel() / (a.elapsed_time(b) * 1e-3) / 1e9
+        del src
+    best = max(rates, key=rates.get)
+    info = {"numa_node": None, "host_nodes": len(nodes), "probed_GBps": {str(k): round(v, 1) for k, v in rates.items()}}
+    if rates[best] > 1.1 * min(rates.values()):
+        os.sched_setaffinity(0, nodes[best])
+        info.update(numa_node=best, cpus=len(nodes[best]), how="probed")
+    else:
+        os.sched_setaffinity(0, all_cpus)
+    return info
 
 
 def run_ours(args):
