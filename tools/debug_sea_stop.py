@@ -1,9 +1,11 @@
+"""Phase timing of the SEA kernel by early exit (OFPSB_DEBUG_SEA_STOP = 1 loads, 2 + window sums, 3 + tile predictor, 0 whole
+kernel); PAIRS=1 gives the latency of a launch that does not fill the machine."""
 import os, sys
 sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 from ofps_b200 import capi, synth
 ctx = capi.Context(0)
-W,H,P=1920,1080,64
+W,H,P=1920,1080,int(os.environ.get('PAIRS','64'))
 fr = synth.make_stream(P+1, W, H, 16)
 d = ctx.dev_alloc(fr.nbytes); de = ctx.dev_alloc(P*8040*16)
 ctx.to_device(d, fr)
