@@ -372,6 +372,11 @@ def run_ours(args):
 
     # ---- frame-by-frame decoder path (ofpsb_stream_*): PAGEABLE caller frames, one frame per call
     pageable = np.array(host.array)                               # plain numpy memory, not page-locked
+    if world > 1 and "OFPSB_COPY_THREADS" not in os.environ:
+        # ranks share the host: the staging-copy threads of a rank (default: up to 8) are cut to its share of the cores
+        # (8 ranks on the pool's 32-core boxes: 2 each instead of 64 spinning threads on 32 cores)
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        os.environ["OFPSB_COPY_THREADS"] = str(max(1, min(8, len(os.sched_getaffinity(0)) // (2 * local_world))))
     st = capi.FrameStream(ctx, W, H, BLOCK, SEARCH, METRIC, depth=6)
     out = np.empty((NBLOCKS, 4), np.float32)
     last = None

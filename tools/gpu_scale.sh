@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
 lscpu | grep -E "^CPU\(s\)|Socket|NUMA node" ; nvidia-smi topo -m 2>/dev/null | head -11 | cut -c1-150
-for n in 8 2; do
+for n in ${@:-8 2}; do
   if [ $n -le $N ]; then
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/bench_ours_n$n.json 2> gpurun_out/bench_ours_n$n.err
     echo "stdout lines: $(wc -l < gpurun_out/bench_ours_n$n.json)"
