@@ -15,7 +15,10 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstring>
+#if defined(__x86_64__) || defined(_M_X64)
 #include <emmintrin.h>
+#define OFPSB_NT_COPY 1
+#endif
 #include <mutex>
 #include <new>
 #include <thread>
@@ -67,6 +70,9 @@ private:
     // measured on the pool's 16-core hosts, pageable 1080p frames: 83 -> 66 us per frame, 24.9 -> 31.4 Gpix/s).
     static void copy_stream(uint8_t* dst, const uint8_t* src, size_t n)
     {
+#ifndef OFPSB_NT_COPY
+        memcpy(dst, src, n);
+#else
         if (n < 4096) {
             memcpy(dst, src, n);
             return;
@@ -87,6 +93,7 @@ private:
         }
         memcpy(dst + i, src + i, n - i);
         _mm_sfence();
+#endif
     }
     static void part(uint8_t* dst, size_t ds, const uint8_t* src, size_t ss, size_t rb, int r0, int r1)
     {
