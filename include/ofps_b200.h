@@ -90,7 +90,16 @@ void *ofpsb_get_stream(ofpsb_ctx *ctx);
  *   "block_match_prune"   1 = exact successive-elimination pruning in front of the exhaustive SAD search
  *                         (default; same results, data-dependent speed), 0 = always exhaustive
  *   "block_match_stats"   1 = count blocks / decided blocks / exact evaluations of the pruning pass
- *   "block_match_chunk_pairs"  pairs per chunk of the pruned path (0 = whole batch in one chunk, default) */
+ *   "block_match_chunk_pairs"  pairs per chunk of the round-1 pruning pipeline (0 = whole batch in one chunk, default)
+ *   "block_match_pruner"  0 = fused SEA kernel (default: SAD, 8x8 / 16x16 blocks, +-8 / +-16 / +-32), 1 = round-1 pipeline
+ *   "block_match_adaptive" 1 = skip the SEA kernel for 15 launches after one that left most blocks undecided (default)
+ *   "block_match_tile_h"  0 = by launch size (default), 32 / 64 = tile rows of the SEA kernel (+-32 always uses 32)
+ *   "block_match_prefetch_tiles"  L2 prefetch distance of the SEA kernel in tiles (-1 = default)
+ *   "block_match_profile" 1 = time the SEA / work-list kernels with events (ofpsb_block_match_kernel_ms)
+ *   "detect_union_find"   1 = union-find detector for every size (default: one-warp flood fill up to 32 x 32 cells)
+ *   "almeida_stepwise"    1 = one launch per solver step instead of the persistent cooperative grid
+ * Environment: OFPSB_COPY_THREADS = host threads (caller included) that copy a pageable frame into the pinned
+ * staging ring of ofpsb_stream_* (default: half the cores, at most 8). */
 int ofpsb_set_option(ofpsb_ctx *ctx, const char *key, long long value);
 
 /* Pinned host memory (page-locked; makes the batched host entry points copy asynchronously) and
