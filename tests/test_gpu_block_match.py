@@ -177,6 +177,36 @@ def test_pruned_equals_exhaustive(ctx, oracle, block, search, w, h, noise):
     np.testing.assert_array_equal(a["cost"], cost)
 
 
+@pytest.mark.parametrize("block", [8, 16])
+def test_wide_range_edge_cases(ctx, oracle, block):
+    """+-32 SEA instances: frames smaller than the search window, periodic and flat content (ties over 65 x 65
+    candidates), content panned by exactly the range and beyond it, saturated pixels, a batch."""
+    cases = []
+    a = synth.textured_plane(3, 64, 48)
+    cases.append((a, np.roll(a, 5, axis=1)))                                    # 64 x 48: every block is a border block
+    per = ((np.arange(160)[:, None] % 6) * 40 + (np.arange(256)[None] % 5) * 9).astype(np.uint8)
+    cases.append((per, np.roll(np.roll(per, 2, axis=0), -4, axis=1)))           # many zero-cost candidates: the shortest wins
+    cases.append((np.full((96, 160), 9, np.uint8), np.full((96, 160), 9, np.uint8)))
+    t = synth.textured_plane(1, 384, 224)
+    cases.append((t, np.roll(np.roll(t, 32, axis=1), -32, axis=0)))             # exactly dx = +R / dy = -R
+    cases.append((t, np.roll(t, 45, axis=1)))                                   # beyond the range
+    hi = np.random.default_rng(5).integers(0, 2, (128, 256)).astype(np.uint8) * 255
+    cases.append((hi, 255 - hi))
+    for prev, cur in cases:
+        got = ctx.block_match(prev, cur, block, 32, 0)
+        mv, cost, ent = oracle.block_match(prev, cur, block, 32, 0, threads=oracle.max_threads(), fast=True)
+        np.testing.assert_array_equal(got["cost"], cost)
+        np.testing.assert_array_equal(got["mv"], mv)
+        assert got["entries"].tobytes() == ent.tobytes()
+        assert np.abs(got["mv"]).max() <= 32
+    fr = synth.make_stream(4, 272, 144, 32, noise_lsb=1)
+    got = ctx.block_match(fr[:-1], fr[1:], block, 32, 0)
+    for i in range(3):
+        mv, cost, _ = oracle.block_match(fr[i], fr[i + 1], block, 32, 0, threads=oracle.max_threads(), fast=True)
+        np.testing.assert_array_equal(got["cost"][i], cost)
+        np.testing.assert_array_equal(got["mv"][i], mv)
+
+
 def test_pruned_batch_and_worst_case(ctx, oracle):
     """Unrelated frames (nothing decided by the bounds) and a batch through the work list."""
     rng = np.random.default_rng(5)
