@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("w,h,block,search,metric,depth", [(640, 360, 16, 8, 0, 3), (1920, 1080, 16, 16, 0, 4),
-                                                           (322, 200, 8, 8, 1, 5), (648, 364, 8, 16, 0, 4)])
+                                                           (322, 200, 8, 8, 1, 5), (648, 364, 8, 16, 0, 4), (768, 432, 8, 32, 0, 4),
+                                                           (1280, 720, 16, 32, 0, 3)])
 def test_stream_push_equals_batch(ctx, oracle, w, h, block, search, metric, depth):
     frames = synth.make_stream(9, w, h, search, noise_lsb=1)
     st = capi.FrameStream(ctx, w, h, block, search, metric, depth)
