@@ -153,7 +153,7 @@ def test_invalid_arguments(ctx):
 
 @pytest.mark.parametrize("noise", [0, 1, 3])
 @pytest.mark.parametrize("block,search,w,h", [(16, 16, 1920, 1080), (8, 32, 768, 432), (16, 8, 640, 360), (8, 8, 320, 208),
-                                              (16, 32, 640, 368), (8, 16, 648, 360)])
+                                              (16, 32, 640, 368), (8, 16, 648, 360), (8, 32, 3840, 2160)])
 def test_pruned_equals_exhaustive(ctx, oracle, block, search, w, h, noise):
     """The successive-elimination front end must not change a single output bit."""
     prev, cur, _ = synth.make_pair(w, h, search, index=11 + noise, noise_lsb=noise)
