@@ -98,6 +98,8 @@ void *ofpsb_get_stream(ofpsb_ctx *ctx);
  *   "block_match_profile" 1 = time the SEA / work-list kernels with events (ofpsb_block_match_kernel_ms)
  *   "detect_union_find"   1 = union-find detector for every size (default: one-warp flood fill up to 32 x 32 cells)
  *   "almeida_stepwise"    1 = one launch per solver step instead of the persistent cooperative grid
+ *   "almeida_cluster"     0 = never use the one-cluster solver (default 1: fields of up to 16,384 vectors run in one
+ *                         thread-block cluster, one entry per thread, partial sums exchanged through DSMEM)
  * Environment: OFPSB_COPY_THREADS = host threads (caller included) that copy a pageable frame into the pinned
  * staging ring of ofpsb_stream_* (default: half the cores, at most 8). */
 int ofpsb_set_option(ofpsb_ctx *ctx, const char *key, long long value);

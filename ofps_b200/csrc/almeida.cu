@@ -20,6 +20,8 @@
 // the host libm, as the CPU path does) and passed by value.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <cmath>
 
 namespace ofpsb {
@@ -112,6 +114,16 @@ __device__ __forceinline__ void quat_from_euler(float roll, float pitch, float y
     q[3] = cr * cp * sy - sr * sp * cy;
 }
 
+// from_euler_angles on half-angle sines / cosines (same expression tree as quat_from_euler: literal 0 / 1 arguments fold the
+// same way)
+__device__ __forceinline__ void quat_from_sincos(float sr, float cr, float sp, float cp, float sy, float cy, float q[4])
+{
+    q[0] = cr * cp * cy + sr * sp * sy;
+    q[1] = sr * cp * cy - cr * sp * sy;
+    q[2] = cr * sp * cy + sr * cp * sy;
+    q[3] = cr * cp * sy - sr * sp * cy;
+}
+
 __device__ __forceinline__ void quat_mul(const float a[4], const float b[4], float o[4])
 {
     const float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
@@ -121,42 +133,60 @@ __device__ __forceinline__ void quat_mul(const float a[4], const float b[4], flo
     o[0] = w; o[1] = i; o[2] = j; o[3] = k;
 }
 
-// Matrix3::lu() with partial pivoting + solve; false when a pivot is zero (almeida:181-183)
-__device__ bool lu3_solve(const float a_in[9], const float b_in[3], float x[3])
+// Matrix3::lu() with partial pivoting + solve; false when a pivot is zero (almeida:181-183).  Every index is a
+// compile-time constant after unrolling (row swaps are conditional swaps of fixed rows, the right-hand side is swapped with
+// the rows instead of being permuted at the end), so the matrix stays in registers: the solver step is one thread's
+// dependent chain between two barriers of every iteration, and the local-memory version cost ~1 us of it.
+__device__ __forceinline__ bool lu3_solve(const float a_in[9], const float b_in[3], float x[3])
 {
-    float a[9], b[3];
-    for (int i = 0; i < 9; i++) a[i] = a_in[i];
-    for (int i = 0; i < 3; i++) b[i] = b_in[i];
-    int perm[3] = {0, 1, 2};
+    float a[3][3], y[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        y[r] = b_in[r];
+#pragma unroll
+        for (int c = 0; c < 3; c++) a[r][c] = a_in[r * 3 + c];
+    }
+#pragma unroll
     for (int i = 0; i < 3; i++) {
         int piv = i;
-        float best = fabsf(a[i * 3 + i]);
+        float best = fabsf(a[i][i]), pv = a[i][i];
+#pragma unroll
         for (int r = i + 1; r < 3; r++) {
-            const float v = fabsf(a[r * 3 + i]);
-            if (v > best) { best = v; piv = r; }
+            const float v = fabsf(a[r][i]);
+            if (v > best) { best = v; piv = r; pv = a[r][i]; }
         }
-        if (a[piv * 3 + i] == 0.0f) continue;
-        if (piv != i) {
-            for (int c = 0; c < 3; c++) { const float t = a[i * 3 + c]; a[i * 3 + c] = a[piv * 3 + c]; a[piv * 3 + c] = t; }
-            const int t = perm[i]; perm[i] = perm[piv]; perm[piv] = t;
-        }
-        const float inv_diag = 1.0f / a[i * 3 + i];
-        for (int r = i + 1; r < 3; r++) a[r * 3 + i] = a[r * 3 + i] * inv_diag;
-        for (int c = i + 1; c < 3; c++) {
-            const float pr = a[i * 3 + c];
-            for (int r = i + 1; r < 3; r++) a[r * 3 + c] = a[r * 3 + c] + (-pr) * a[r * 3 + i];
+        if (pv != 0.0f) {
+#pragma unroll
+            for (int r = i + 1; r < 3; r++)
+                if (piv == r) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { const float t = a[i][c]; a[i][c] = a[r][c]; a[r][c] = t; }
+                    const float t = y[i]; y[i] = y[r]; y[r] = t;
+                }
+            const float inv_diag = 1.0f / a[i][i];
+#pragma unroll
+            for (int r = i + 1; r < 3; r++) a[r][i] = a[r][i] * inv_diag;
+#pragma unroll
+            for (int c = i + 1; c < 3; c++) {
+                const float pr = a[i][c];
+#pragma unroll
+                for (int r = i + 1; r < 3; r++) a[r][c] = a[r][c] + (-pr) * a[r][i];
+            }
         }
     }
-    float y[3] = {b[perm[0]], b[perm[1]], b[perm[2]]};
+#pragma unroll
     for (int i = 0; i < 2; i++) {
         const float coeff = y[i];
-        for (int r = i + 1; r < 3; r++) y[r] = y[r] + (-coeff) * a[r * 3 + i];
+#pragma unroll
+        for (int r = i + 1; r < 3; r++) y[r] = y[r] + (-coeff) * a[r][i];
     }
+#pragma unroll
     for (int i = 2; i >= 0; i--) {
-        const float d = a[i * 3 + i];
+        const float d = a[i][i];
         if (d == 0.0f) return false;
         y[i] = y[i] / d;
-        for (int r = 0; r < i; r++) y[r] = y[r] + (-y[i]) * a[r * 3 + i];
+#pragma unroll
+        for (int r = 0; r < i; r++) y[r] = y[r] + (-y[i]) * a[r][i];
     }
     x[0] = y[0]; x[1] = y[1]; x[2] = y[2];
     return true;
@@ -177,6 +207,36 @@ __device__ void lsq_step(const float a[9], const float b[3], float eps_r, int it
     quat_mul(pr, yaw, rot);
     quat_mul(rotation, rot, nr);
     for (int k = 0; k < 4; k++) rotation[k] = nr[k];
+}
+
+// The same step taken by a whole warp (all 32 lanes call it converged; a, b, rotation are lane 0's): lane 0 solves the 3x3
+// system, lanes 0-2 take the sine and cosine of one angle each — six libm calls in a row are most of the scalar step —
+// and lane 0 composes the rotation.  Same operations on the same values as lsq_step.
+__device__ __forceinline__ void lsq_step_warp(const float a[9], const float b[3], float eps_r, int it, float rotation[4], int lane)
+{
+    const float alpha = (it == LSQ_ITERS - 1) ? 1.0f : ALPHA;   // almeida:138
+    float model[3] = {0.0f, 0.0f, 0.0f};
+    if (lane == 0) {
+        if (!lu3_solve(a, b, model)) model[0] = model[1] = model[2] = 0.0f;
+        for (int k = 0; k < 3; k++) model[k] = model[k] * eps_r * alpha;
+    }
+    const float m0 = __shfl_sync(0xffffffffu, model[0], 0), m1 = __shfl_sync(0xffffffffu, model[1], 0);
+    const float m2 = __shfl_sync(0xffffffffu, model[2], 0);
+    const float ang = lane == 0 ? m0 : lane == 1 ? m1 : -m2;
+    const float sn = sinf(ang * 0.5f), cs = cosf(ang * 0.5f);
+    const float s0 = __shfl_sync(0xffffffffu, sn, 0), c0 = __shfl_sync(0xffffffffu, cs, 0);
+    const float s1 = __shfl_sync(0xffffffffu, sn, 1), c1 = __shfl_sync(0xffffffffu, cs, 1);
+    const float s2 = __shfl_sync(0xffffffffu, sn, 2), c2 = __shfl_sync(0xffffffffu, cs, 2);
+    if (lane == 0) {
+        float roll[4], pitch[4], yaw[4], pr[4], rot[4], nr[4];
+        quat_from_sincos(0.0f, 1.0f, s0, c0, 0.0f, 1.0f, roll);    // quat_from_euler(0, model[0], 0)
+        quat_from_sincos(s1, c1, 0.0f, 1.0f, 0.0f, 1.0f, pitch);   // quat_from_euler(model[1], 0, 0)
+        quat_from_sincos(0.0f, 1.0f, 0.0f, 1.0f, s2, c2, yaw);     // quat_from_euler(0, 0, -model[2])
+        quat_mul(pitch, roll, pr);
+        quat_mul(pr, yaw, rot);
+        quat_mul(rotation, rot, nr);
+        for (int k = 0; k < 4; k++) rotation[k] = nr[k];
+    }
 }
 
 // the four vectors of one entry (almeida:142-157)
@@ -283,19 +343,22 @@ __global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __re
         }
         __syncthreads();
         if (SINGLE) {
-            if (tid == 0) {
-                float a[9], b[3];
-                for (int k = 0; k < 12; k++) {
-                    if (k < k0) continue;
-                    double s = 0.0;
-                    for (int w = 0; w < LSQ_NT / 32; w++) s += red[w][k];
-                    if (k < 9) s_a[k] = (float)s;
-                    else b[k - 9] = (float)s;
+            if (tid < 32) {   // warp 0 takes the step (the values are lane 0's)
+                float a[9] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, b[3] = {0.0f, 0.0f, 0.0f};
+                if (tid == 0) {
+                    for (int k = 0; k < 12; k++) {
+                        if (k < k0) continue;
+                        double s = 0.0;
+                        for (int w = 0; w < LSQ_NT / 32; w++) s += red[w][k];
+                        if (k < 9) s_a[k] = (float)s;
+                        else b[k - 9] = (float)s;
+                    }
+                    for (int k = 0; k < 9; k++) a[k] = s_a[k];
                 }
-                for (int k = 0; k < 9; k++) a[k] = s_a[k];
                 float r4[4] = {s_rot[0], s_rot[1], s_rot[2], s_rot[3]};
-                lsq_step(a, b, cst.eps_r, it, r4);
-                for (int k = 0; k < 4; k++) s_rot[k] = r4[k];
+                lsq_step_warp(a, b, cst.eps_r, it, r4, tid);
+                if (tid == 0)
+                    for (int k = 0; k < 4; k++) s_rot[k] = r4[k];
             }
             __syncthreads();
         } else if (PERSIST) {
@@ -320,14 +383,17 @@ __global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __re
             __syncthreads();
             combine_partials(buf, gridDim.x, k0, red, tid);
             __syncthreads();
-            if (tid == 0) {
+            if (tid < 32) {
                 float a[9], b[3];
                 for (int k = 0; k < 9; k++) a[k] = first ? (float)red[0][k] : s_a[k];
                 for (int k = 0; k < 3; k++) b[k] = (float)red[0][9 + k];
                 float r4[4] = {s_rot[0], s_rot[1], s_rot[2], s_rot[3]};
-                lsq_step(a, b, cst.eps_r, it, r4);
-                for (int k = 0; k < 4; k++) s_rot[k] = r4[k];
-                if (first) for (int k = 0; k < 9; k++) s_a[k] = a[k];
+                __syncwarp();   // every lane has read s_a / s_rot before lane 0 rewrites them
+                lsq_step_warp(a, b, cst.eps_r, it, r4, tid);
+                if (tid == 0) {
+                    for (int k = 0; k < 4; k++) s_rot[k] = r4[k];
+                    if (first) for (int k = 0; k < 9; k++) s_a[k] = a[k];
+                }
             }
             s_last = blockIdx.x == 0;
             __syncthreads();
@@ -349,15 +415,18 @@ __global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __re
                 __syncthreads();   // red[][] of the block reduction has been consumed
                 combine_partials(partial, gridDim.x, k0, red, tid);
                 __syncthreads();
-                if (tid == 0) {
+                if (tid < 32) {
                     float a[9], b[3];
                     for (int k = 0; k < 9; k++) a[k] = first ? (float)red[0][k] : s_a[k];
                     for (int k = 0; k < 3; k++) b[k] = (float)red[0][9 + k];
                     float r4[4] = {s_rot[0], s_rot[1], s_rot[2], s_rot[3]};
-                    lsq_step(a, b, cst.eps_r, it, r4);
-                    for (int k = 0; k < 4; k++) { state->rotation[k] = r4[k]; s_rot[k] = r4[k]; }
-                    if (first) for (int k = 0; k < 9; k++) state->a[k] = a[k];
-                    state->ticket = 0;
+                    __syncwarp();
+                    lsq_step_warp(a, b, cst.eps_r, it, r4, tid);
+                    if (tid == 0) {
+                        for (int k = 0; k < 4; k++) { state->rotation[k] = r4[k]; s_rot[k] = r4[k]; }
+                        if (first) for (int k = 0; k < 9; k++) state->a[k] = a[k];
+                        state->ticket = 0;
+                    }
                 }
                 __syncthreads();
             }
@@ -365,6 +434,116 @@ __global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __re
     }
     // rotation.inverse() (almeida:199)
     if ((SINGLE || (s_last && (PERSIST || it_arg == LSQ_ITERS - 1))) && tid == 0) {
+        out_quat[0] = s_rot[0]; out_quat[1] = -s_rot[1]; out_quat[2] = -s_rot[2]; out_quat[3] = -s_rot[3];
+    }
+}
+
+// ------------------------------------------------------------------ least-squares kernel, one thread-block cluster
+// The reference's own field sizes (a few thousand to 12,600 vectors) are latency-bound in the grid version above: ~6 us
+// per iteration, of which ~0.3 us is arithmetic and the rest is the trip of the partial sums through L2 (publish, fence,
+// ticket, poll, re-read).  Here ONE cluster of up to 16 CTAs x 1024 threads holds one entry per thread for all 30
+// iterations: the un-projected point and the three prototype vectors of the entry — iteration-invariant, recomputed
+// every iteration by the reference and by the kernels above — stay in registers, so an iteration is one delta() and
+// three dot products per thread; the per-CTA sums go straight into every CTA's shared memory (DSMEM stores), the
+// hardware cluster barrier replaces the L2 ticket, and every CTA takes the identical solver step.  Partials are
+// double-buffered by iteration parity (a CTA can be one iteration ahead of a slow reader, never two: the next barrier
+// needs everybody).  Sums are f64 in a fixed order (lanes by shuffle tree, warps, then CTAs ascending).
+constexpr int CL_NT = 1024;
+constexpr int CL_MAX_CTAS = 16;
+
+__global__ void __launch_bounds__(CL_NT, 1) almeida_lsq_cluster_kernel(const ofps_mv* __restrict__ entries,
+                                                                      const uint32_t* __restrict__ idx, size_t n_arg,
+                                                                      const uint32_t* __restrict__ n_ptr,
+                                                                      const AlmeidaConst cst, float* __restrict__ out_quat)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double red[CL_NT / 32][12];
+    __shared__ double part[2][CL_MAX_CTAS][12];   // [parity][CTA of the cluster][component], written by the owners
+    __shared__ float s_rot[4];
+    __shared__ float s_a[9];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned rank = cluster.block_rank(), ncta = cluster.num_blocks();
+    const size_t n = n_ptr ? (size_t)*n_ptr : n_arg;
+    if (n_ptr && n < 3) {   // solve_ypr_ransac: fewer than 3 inliers -> identity (almeida:246-250); cluster-uniform
+        if (rank == 0 && tid == 0) { out_quat[0] = 1.0f; out_quat[1] = 0.0f; out_quat[2] = 0.0f; out_quat[3] = 0.0f; }
+        return;
+    }
+    if (tid < 4) s_rot[tid] = tid == 0 ? 1.0f : 0.0f;
+    // this thread's entry: world point and prototypes once (almeida:151-153 recomputes them every iteration)
+    const size_t i = (size_t)rank * blockDim.x + tid;
+    const bool have = i < n;
+    float4 e = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float w[3] = {0.0f, 0.0f, 1.0f}, p1[2] = {0.0f, 0.0f}, p2[2] = {0.0f, 0.0f}, p3[2] = {0.0f, 0.0f};
+    if (have) {
+        e = __ldg(reinterpret_cast<const float4*>(entries) + (idx ? idx[i] : i));
+        unproject_world(cst, e.x, e.y, w);
+        delta_from_world(cst, w, cst.roll, e.x, e.y, p1);
+        delta_from_world(cst, w, cst.pitch, e.x, e.y, p2);
+        delta_from_world(cst, w, cst.yaw, e.x, e.y, p3);
+    }
+    __syncthreads();
+
+    for (int it = 0; it < LSQ_ITERS; it++) {
+        const bool first = it == 0;
+        const int k0 = first ? 0 : 9;
+        double acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) acc[k] = 0.0;
+        if (have) {
+            const float rot[4] = {s_rot[0], s_rot[1], s_rot[2], s_rot[3]};
+            float rotm[9], d[2];
+            quat_to_mat3(rot, rotm);
+            delta_from_world(cst, w, rotm, e.x, e.y, d);
+            const float v0[2] = {e.z - d[0], e.w - d[1]};
+            const float* pv[3] = {p1, p2, p3};
+            if (first) {
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) acc[r * 3 + c] = (double)(pv[r][0] * pv[c][0] + pv[r][1] * pv[c][1]);
+            }
+#pragma unroll
+            for (int r = 0; r < 3; r++) acc[9 + r] = (double)(pv[r][0] * v0[0] + pv[r][1] * v0[1]);
+        }
+        for (int k = k0; k < 12; k++) {
+            const double sum = warp_sum(acc[k]);
+            if (lane == 0) red[warp][k] = sum;
+        }
+        __syncthreads();
+        // CTA total of component k (thread k), stored into every CTA's part[parity][rank][k]
+        if (tid < 12 && tid >= k0) {
+            double sum = 0.0;
+            for (int wv = 0; wv < (int)(blockDim.x >> 5); wv++) sum += red[wv][tid];
+            for (unsigned r = 0; r < ncta; r++) *cluster.map_shared_rank(&part[it & 1][rank][tid], r) = sum;
+        }
+        cluster.sync();   // release / acquire across the cluster: every CTA's partials have landed everywhere
+        if (tid < 32) {
+            // lanes k0 .. 11 add up the CTA partials of one component each (CTAs ascending), lane 0 collects them
+            double sum = 0.0;
+            if (tid >= k0 && tid < 12)
+                for (unsigned r = 0; r < ncta; r++) sum += part[it & 1][r][tid];
+            float a[9], b[3];
+            const float fs = (float)sum;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const float v = __shfl_sync(0xffffffffu, fs, k);
+                a[k] = first ? v : s_a[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) b[k] = __shfl_sync(0xffffffffu, fs, 9 + k);
+            float r4[4] = {s_rot[0], s_rot[1], s_rot[2], s_rot[3]};
+            __syncwarp();
+            lsq_step_warp(a, b, cst.eps_r, it, r4, tid);
+            if (tid == 0) {
+                for (int k = 0; k < 4; k++) s_rot[k] = r4[k];
+                if (first) for (int k = 0; k < 9; k++) s_a[k] = a[k];
+            }
+        }
+        __syncthreads();
+    }
+    cluster.sync();   // no CTA exits while another may still store into its shared memory
+    if (rank == 0 && tid == 0) {   // rotation.inverse() (almeida:199)
         out_quat[0] = s_rot[0]; out_quat[1] = -s_rot[1]; out_quat[2] = -s_rot[2]; out_quat[3] = -s_rot[3];
     }
 }
@@ -600,10 +779,52 @@ int run_lsq(const ofps_mv* d_entries, const uint32_t* d_idx, size_t n, const uin
         if (launches) ++*launches;
         return OFPSB_OK;
     }
-    // a co-resident grid: the device can hold `per_sm` CTAs per SM at once
-    static int per_sm_cached[64] = {};
     int dev = 0;
     OFPSB_CUDA_TRY(cudaGetDevice(&dev));
+    // up to 16 x 1024 entries: one thread-block cluster, one entry per thread (sizes 1, 2, 4, 8 are portable, 16 needs the
+    // opt-in and a GPC with 16 free SMs: checked once per device)
+    if (n <= (size_t)CL_MAX_CTAS * CL_NT && !s.no_cooperative && !s.no_cluster) {
+        static int cluster_ok[64] = {};   // 0 unknown, 1 yes, -1 no
+        // as many CTAs as the cluster may have once there are 64 entries for each: an iteration is bound by what ONE SM has to
+        // do (1024 threads: ~1,000 cycles of shuffles for the f64 warp sums alone), not by the exchange
+        unsigned ncta = 1;
+        while (ncta < (unsigned)CL_MAX_CTAS && (size_t)ncta * 64 < n) ncta *= 2;
+        const unsigned nt = (unsigned)(((n + ncta - 1) / ncta + 31) / 32 * 32);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ncta);
+        cfg.blockDim = dim3(nt < 32 ? 32 : nt);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ncta;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int& ok = cluster_ok[dev & 63];
+        if (ok == 0) {
+            ok = -1;
+            if (cudaFuncSetAttribute(almeida_lsq_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                cudaLaunchConfig_t probe = cfg;
+                probe.gridDim = dim3(CL_MAX_CTAS);
+                probe.blockDim = dim3(CL_NT);
+                cudaLaunchAttribute pa[1] = {attr[0]};
+                pa[0].val.clusterDim.x = CL_MAX_CTAS;
+                probe.attrs = pa;
+                int nclusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&nclusters, almeida_lsq_cluster_kernel, &probe) == cudaSuccess && nclusters >= 1) ok = 1;
+            }
+            cudaGetLastError();
+        }
+        if (ok == 1 &&
+            cudaLaunchKernelEx(&cfg, almeida_lsq_cluster_kernel, d_entries, d_idx, n, d_n_ptr, cst, d_quat) == cudaSuccess) {
+            if (launches) ++*launches;
+            return OFPSB_OK;
+        }
+        cudaGetLastError();
+    }
+    // a co-resident grid: the device can hold `per_sm` CTAs per SM at once
+    static int per_sm_cached[64] = {};
     int per_sm = dev >= 0 && dev < 64 ? per_sm_cached[dev] : 0;
     if (per_sm == 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, almeida_lsq_kernel<LSQ_PERSISTENT>, LSQ_NT, 0) != cudaSuccess ||

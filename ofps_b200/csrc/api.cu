@@ -388,6 +388,7 @@ int ofpsb_set_option(ofpsb_ctx* ctx, const char* key, long long value)
     }
     else if (!strcmp(key, "detect_union_find") && value >= 0 && value <= 1) ctx->opt_detect_union_find = (int)value;
     else if (!strcmp(key, "almeida_stepwise") && value >= 0 && value <= 1) ctx->almeida.no_cooperative = value != 0;
+    else if (!strcmp(key, "almeida_cluster") && value >= 0 && value <= 1) ctx->almeida.no_cluster = value == 0;
     else if (!strcmp(key, "block_match_pruner") && value >= 0 && value <= 1) ctx->bm_scratch.pruner = (int)value;
     else if (!strcmp(key, "block_match_chunk_pairs") && value >= 0 && value <= 32768) ctx->bm_scratch.chunk_pairs = (int)value;
     else {

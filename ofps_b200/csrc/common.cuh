@@ -152,6 +152,7 @@ void interpolate_empty_cells_host(float* sums, float* counts, size_t w, size_t h
 struct AlmeidaScratch {
     DevBuf state, partial, hyp, inlier_idx, flags;
     bool no_cooperative = false;   // tests: force the one-launch-per-iteration fallback of the multi-CTA solver
+    bool no_cluster = false;       // tests: skip the one-cluster solver (option "almeida_cluster" = 0)
 };
 
 int launch_almeida(const ofps_mv* d_entries, size_t n, float aspect, float fov_y_deg, int use_ransac,

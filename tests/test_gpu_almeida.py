@@ -96,6 +96,14 @@ def test_ransac_rejects_outliers(ctx, oracle):
 def test_persistent_grid_equals_stepwise_launches(ctx):
     """The one-launch co-resident grid (grid barrier per iteration) and the one-launch-per-iteration fallback run the
     same blocks in the same reduction order: identical bits."""
+    ctx.set_option("almeida_cluster", 0)       # 12,600 entries would otherwise take the one-cluster solver
+    try:
+        _persistent_equals_stepwise(ctx)
+    finally:
+        ctx.set_option("almeida_cluster", 1)
+
+
+def _persistent_equals_stepwise(ctx):
     for w, h in ((150, 84), (640, 360)):
         field, _ = synth.rotation_field(w, h, 16 / 9, 22.275, (0.4, -0.1, 0.25))
         a = ctx.almeida(field, 16 / 9, 22.275)
@@ -113,6 +121,32 @@ def test_persistent_grid_equals_stepwise_launches(ctx):
         finally:
             ctx.set_option("almeida_stepwise", 0)
         assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("w,h", [(30, 20), (40, 30), (50, 50), (128, 64), (91, 91), (150, 84), (128, 128), (129, 128)])
+def test_cluster_solver(ctx, oracle, w, h):
+    """The one-cluster solver (one entry per thread, prototypes cached, partial sums through DSMEM; fields of up to
+    16,384 vectors) against the multi-CTA grid (same f32 arithmetic per entry, f64 sums grouped differently: 1e-6) and
+    against the f64 oracle (1e-4); cluster sizes 1, 2, 4, 8, 16 and the first size that no longer fits."""
+    field, q_truth = synth.rotation_field(w, h, 16 / 9, 22.275, (0.25, -0.3, 0.15))
+    a = ctx.almeida(field, 16 / 9, 22.275)
+    ctx.set_option("almeida_cluster", 0)
+    try:
+        b = ctx.almeida(field, 16 / 9, 22.275)
+    finally:
+        ctx.set_option("almeida_cluster", 1)
+    assert quat_close(a, b) < 1e-6, (a, b)
+    q64 = oracle.almeida_lsq_f64(field, 16 / 9, 22.275)
+    assert quat_close(a, q64) < TOL, (a, q64)
+    # RANSAC: the refit over the inliers (count known only on the device) goes through the same solver
+    bad = synth.corrupt_field(field, 0.2)
+    qa = ctx.almeida(bad, 16 / 9, 22.275, use_ransac=True, num_iters=50, ransac_samples=4000, seed=3)
+    ctx.set_option("almeida_cluster", 0)
+    try:
+        qb = ctx.almeida(bad, 16 / 9, 22.275, use_ransac=True, num_iters=50, ransac_samples=4000, seed=3)
+    finally:
+        ctx.set_option("almeida_cluster", 1)
+    assert quat_close(qa, qb) < 1e-6, (qa, qb)
 
 
 def test_config3_full_1080p_against_f64_oracle(ctx, oracle):
