@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(LSQ_NT) almeida_lsq_kernel(const ofps_mv* __re
                     for (int k = 0; k < 9; k++) a[k] = s_a[k];
                 }
                 float r4[4] = {s_rot[0], s_rot[1], s_rot[2], s_rot[3]};
+                __syncwarp();   // every lane has read s_rot before lane 0 rewrites it
                 lsq_step_warp(a, b, cst.eps_r, it, r4, tid);
                 if (tid == 0)
                     for (int k = 0; k < 4; k++) s_rot[k] = r4[k];
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(CL_NT, 1) almeida_lsq_cluster_kernel(const ofp
         delta_from_world(cst, w, cst.pitch, e.x, e.y, p2);
         delta_from_world(cst, w, cst.yaw, e.x, e.y, p3);
     }
-    __syncthreads();
+    cluster.sync();   // every CTA of the cluster is running before anyone stores into its shared memory (also the CTA barrier)
 
     for (int it = 0; it < LSQ_ITERS; it++) {
         const bool first = it == 0;

@@ -1,6 +1,6 @@
 """Target for compute-sanitizer (memcheck / racecheck) over the round-2 kernels: the fused SEA block matcher (both tile
 heights, every tuned geometry, frame borders, strips with peer halos, batch mode), the low-latency work-list instance, the
-streaming decoder, the one-warp detector, the staged-id densifier and the persistent Almeida grid; results are compared
+streaming decoder, the one-warp detector, the staged-id densifier, the one-cluster and the persistent-grid Almeida solvers; results are compared
 with the oracle as they go.
 
     compute-sanitizer --tool memcheck  python tools/sanitize_k1.py
@@ -91,9 +91,15 @@ def main():
     got, exp = ctx.detect_block_motion(ent), oracle.detect_block_motion(ent)
     assert got[:3] == tuple(exp[:3]) and got[3].tobytes() == exp[3].tobytes()
     fld, q_truth = synth.rotation_field(64, 36, 16 / 9, 22.275, (0.3, -0.2, 0.1))
-    q = ctx.almeida(fld, 16 / 9, 22.275)
     q64 = oracle.almeida_lsq_f64(fld, 16 / 9, 22.275)
-    assert min(np.abs(q - q64).max(), np.abs(q + q64).max()) < 1e-4
+    for cluster in (1, 0):      # the one-cluster solver (16 CTAs, DSMEM partial sums), then the persistent grid
+        ctx.set_option("almeida_cluster", cluster)
+        q = ctx.almeida(fld, 16 / 9, 22.275)
+        assert min(np.abs(q - q64).max(), np.abs(q + q64).max()) < 1e-4
+        checks += 1
+    ctx.set_option("almeida_cluster", 1)
+    bad = synth.corrupt_field(fld, 0.2)
+    ctx.almeida(bad, 16 / 9, 22.275, use_ransac=True, num_iters=20, ransac_samples=500, seed=3)   # refit: device-side count
     checks += 2
     print(f"sanitize_k1: {checks} checks passed")
     ctx.close()
