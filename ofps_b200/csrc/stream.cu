@@ -271,10 +271,21 @@ int ofpsb_stream_submit(ofpsb_stream* s, const uint8_t* frame, size_t stride)
     } else {
         uint8_t* stage = s->h_frames + s->frame_bytes * slot;
         if (k >= s->depth) OFPSB_CUDA_TRY(cudaEventSynchronize(s->h2d_done[(size_t)slot]));   // its last upload has left
-        if (s->pool) s->pool->copy(stage, s->stride, frame, stride, s->w, s->h);
-        else
-            for (int r = 0; r < s->h; r++) memcpy(stage + (size_t)r * s->stride, frame + (size_t)r * stride, s->w);
-        OFPSB_CUDA_TRY(cudaMemcpyAsync(d_frame, stage, (size_t)s->stride * s->h, cudaMemcpyHostToDevice, ctx->copy_stream));
+        // Nothing in flight (the caller collects every result before the next frame: the synchronous Decoder shape): the
+        // frame goes in four row bands, each handed to the copy engine as soon as it is staged, so the upload of band i
+        // runs behind the host copy of band i+1.  With results outstanding the next frame's staging already overlaps this
+        // frame's upload, and one copy call per frame is cheaper.
+        const int bands = (k - 1 - s->collected <= 0 && s->pool && s->frame_bytes >= (1u << 20)) ? 4 : 1;
+        for (int bnd = 0; bnd < bands; bnd++) {
+            const int r0 = (int)((long long)s->h * bnd / bands), r1 = (int)((long long)s->h * (bnd + 1) / bands);
+            uint8_t* st = stage + (size_t)r0 * s->stride;
+            const uint8_t* src = frame + (size_t)r0 * stride;
+            if (s->pool) s->pool->copy(st, s->stride, src, stride, s->w, r1 - r0);
+            else
+                for (int r = 0; r < r1 - r0; r++) memcpy(st + (size_t)r * s->stride, src + (size_t)r * stride, s->w);
+            OFPSB_CUDA_TRY(cudaMemcpyAsync(d_frame + (size_t)r0 * s->stride, st, (size_t)s->stride * (r1 - r0), cudaMemcpyHostToDevice,
+                                           ctx->copy_stream));
+        }
     }
     OFPSB_CUDA_TRY(cudaEventRecord(s->h2d_done[(size_t)slot], ctx->copy_stream));
     cudaStream_t cs = s->comp[k & 1];

@@ -27,7 +27,15 @@ for name, src in (("pageable", frames), ("pinned", pin.array)):
         while st.collect(out) is not None:
             pass
         t_all = time.perf_counter() - t_all
+    # synchronous form: ofpsb_stream_push returns the result of the frame it was given
+    st2 = capi.FrameStream(ctx, W, H, 16, 16, 0, depth=4)
+    for rep in range(3):
+        t_sync = time.perf_counter()
+        for i in range(len(src)):
+            st2.push(src[i])
+        t_sync = time.perf_counter() - t_sync
+    st2.close()
     n = len(src)
-    print(json.dumps({"frames": name, "submit_us": 1e6 * ts / n, "collect_us": 1e6 * tc / n, "per_frame_us": 1e6 * t_all / n,
+    print(json.dumps({"frames": name, "sync_push_us": 1e6 * t_sync / n, "submit_us": 1e6 * ts / n, "collect_us": 1e6 * tc / n, "per_frame_us": 1e6 * t_all / n,
                       "Gpix_s": W * H * n / t_all / 1e9}), flush=True)
     st.close()
