@@ -127,7 +127,8 @@ def _persistent_equals_stepwise(ctx):
 def test_cluster_solver(ctx, oracle, w, h):
     """The one-cluster solver (one entry per thread, prototypes cached, partial sums through DSMEM; fields of up to
     16,384 vectors) against the multi-CTA grid (same f32 arithmetic per entry, f64 sums grouped differently: 1e-6) and
-    against the f64 oracle (1e-4); cluster sizes 1, 2, 4, 8, 16 and the first size that no longer fits."""
+    against the f64 oracle (1e-4): 38 to 1,024 entries per CTA of the 16-CTA cluster, and the first size that no longer
+    fits (it takes the grid kernel)."""
     field, q_truth = synth.rotation_field(w, h, 16 / 9, 22.275, (0.25, -0.3, 0.15))
     a = ctx.almeida(field, 16 / 9, 22.275)
     ctx.set_option("almeida_cluster", 0)
