@@ -376,6 +376,7 @@ int ofpsb_set_option(ofpsb_ctx* ctx, const char* key, long long value)
     else if (!strcmp(key, "block_match_adaptive") && value >= 0 && value <= 1) {
         ctx->bm_scratch.adaptive = (int)value;
         ctx->bm_scratch.skip_calls = 0;
+        ctx->bm_scratch.over_streak = 0;
         ctx->bm_scratch.listed_total = 0;
     }
     else if (!strcmp(key, "block_match_tile_h") && (value == 0 || value == 32 || value == 64)) ctx->bm_scratch.tile_h = (int)value;

@@ -1073,7 +1073,14 @@ int launch_block_match_sea(const BlockMatchParams& p, BlockMatchScratch& sc, int
     if (sc.adaptive && !peer && !sc.collect_stats) {
         if (sc.ev_listed && sc.listed_total > 0 && cudaEventQuery(sc.ev_listed) == cudaSuccess) {
             // the +-32 kernel costs a larger share of the exhaustive search it replaces (4K 8x8: 0.5-0.8 on noisy content)
-            if ((double)sc.h_listed[0] > (p.range > 16 ? 0.3 : 0.6) * (double)sc.listed_total) sc.skip_calls = 15;
+            // two launches in a row over the threshold (a scene cut in a frame-by-frame stream is ONE bad pair and must not
+            // send the next 15 good ones to the exhaustive kernel); the streak survives the skipped launches, so on steadily
+            // noisy content one probe launch in 16 keeps checking
+            if ((double)sc.h_listed[0] > (p.range > 16 ? 0.3 : 0.6) * (double)sc.listed_total) {
+                if (++sc.over_streak >= 2) sc.skip_calls = 15;
+            } else {
+                sc.over_streak = 0;
+            }
             sc.listed_total = 0;
         }
         cudaGetLastError();

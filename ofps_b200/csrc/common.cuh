@@ -87,6 +87,7 @@ struct BlockMatchScratch {
     cudaEvent_t ev_listed = nullptr;
     long long listed_total = 0;         // blocks of that launch
     int skip_calls = 0;                 // SEA launches still to skip
+    int over_streak = 0;                // consecutive SEA launches that left most blocks undecided
     int adaptive = 1;
     int tile_h = 0;           // SEA kernel tile height: 0 = by launch size, 32 / 64 = forced (tests, A-B)
     int prefetch_tiles = -1;  // SEA kernel: L2 prefetch distance in tiles (-1 = three CTAs per SM, 0 = off)

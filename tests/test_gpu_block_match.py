@@ -207,6 +207,36 @@ def test_wide_range_edge_cases(ctx, oracle, block):
         np.testing.assert_array_equal(got["mv"][i], mv)
 
 
+def test_content_feedback_needs_two_bad_launches(ctx):
+    """Content feedback of the SEA path (block_match_sea.cu): a launch that leaves most blocks to the exhaustive kernel
+    is remembered; two in a row send the next 15 launches straight to the exhaustive kernel (1 kernel launch instead
+    of 2), a single one — a scene cut in a frame-by-frame stream — does not.  Results are identical either way."""
+    rng = np.random.default_rng(11)
+    a, b = (rng.integers(0, 256, (360, 640), dtype=np.uint8) for _ in range(2))     # unrelated: nothing is decided by bounds
+    good = synth.make_stream(3, 640, 360, 16)
+    ctx.set_option("block_match_adaptive", 1)                                       # also clears the state
+
+    def launches(prev, cur):
+        n0 = ctx.launch_count()
+        r = ctx.block_match(prev, cur, 16, 16, 0)
+        ctx.sync()
+        return ctx.launch_count() - n0, r
+
+    ref_bad = None
+    seen = []
+    for i in range(6):
+        n, r = launches(a, b)
+        seen.append(n)
+        if ref_bad is None:
+            ref_bad = r
+        assert r["entries"].tobytes() == ref_bad["entries"].tobytes()
+    assert seen[:2] == [2, 2] and seen[2:] == [1, 1, 1, 1], seen                    # the third launch on is skipped
+    ctx.set_option("block_match_adaptive", 1)
+    a2 = np.roll(a, 3, axis=1)                                                      # the second scene pans: a good pair
+    seen = [launches(*p)[0] for p in ((good[0], good[1]), (good[1], a), (a, a2), (a2, good[0]), (good[0], good[1]))]
+    assert seen == [2, 2, 2, 2, 2], seen                                            # isolated bad pairs (cuts) never trigger it
+
+
 def test_pruned_batch_and_worst_case(ctx, oracle):
     """Unrelated frames (nothing decided by the bounds) and a batch through the work list."""
     rng = np.random.default_rng(5)
