@@ -181,3 +181,37 @@ def test_sea_strips(emu, oracle):
         r = res[0]
         np.testing.assert_array_equal(cost[0][r], ocost[sl][r])
         np.testing.assert_array_equal(mv[0][r], omv[sl][r])
+
+
+def test_sea_randomized_geometries(emu, oracle):
+    """Seeded random geometries and contents through every instance of the kernel (block 8 / 16, range 8 / 16 / 32, both
+    tile heights): widths that are not multiples of the tile, frames smaller than the search window, pans, local motion,
+    noise, strips at random offsets."""
+    rng = np.random.default_rng(20260)
+    for case in range(10):
+        block = int(rng.choice([8, 16]))
+        search = int(rng.choice([8, 16, 32]))
+        w = int(rng.integers(4, 30)) * 16
+        h = int(rng.integers(3, 14)) * 16
+        base = synth.textured_plane(int(rng.integers(1, 1000)), w + 64, h + 64)
+        dx, dy = (int(v) for v in rng.integers(-search, search + 1, 2))
+        prev = base[32:32 + h, 32:32 + w].copy()
+        cur = base[32 + dy:32 + dy + h, 32 + dx:32 + dx + w].copy()
+        if rng.random() < 0.5:                                            # a rectangle with its own motion
+            y0, x0 = int(rng.integers(0, h // 2)), int(rng.integers(0, w // 2))
+            cur[y0:y0 + h // 3, x0:x0 + w // 3] = np.roll(prev, (int(rng.integers(-5, 6)), int(rng.integers(-5, 6))), (0, 1))[y0:y0 + h // 3, x0:x0 + w // 3]
+        noise = int(rng.integers(0, 3))
+        if noise:
+            cur = np.clip(cur.astype(np.int16) + rng.integers(-noise, noise + 1, cur.shape), 0, 255).astype(np.uint8)
+        th = int(rng.choice([32, 64]))
+        check(emu, oracle, prev, cur, block, search, tile_h=th)
+        rows = (h // block // 2) * block
+        if rows >= block and h - rows >= block:                           # the lower part as a strip with its halo
+            omv, ocost, _ = oracle.block_match(prev, cur, block, search, 0, threads=oracle.max_threads(), fast=True)
+            y0 = h - rows - ((h - rows) % block)
+            y0 -= y0 % block
+            mv, cost, ent, res, _ = run_sea(emu, prev, cur, block, search, strip=(y0, (h - y0) // block * block), tile_h=th)
+            sl = slice(y0 // block, y0 // block + mv.shape[1])
+            r = res[0]
+            np.testing.assert_array_equal(cost[0][r], ocost[sl][r])
+            np.testing.assert_array_equal(mv[0][r], omv[sl][r])
