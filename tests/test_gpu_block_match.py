@@ -207,6 +207,35 @@ def test_wide_range_edge_cases(ctx, oracle, block):
         np.testing.assert_array_equal(got["mv"][i], mv)
 
 
+def test_pruned_randomized(ctx):
+    """Seeded random frame sizes, contents, batch sizes and geometries: the SEA path against the exhaustive kernel, bit for
+    bit (the exhaustive kernel is checked against the oracle above)."""
+    rng = np.random.default_rng(77)
+    ctx.set_option("block_match_adaptive", 0)
+    try:
+        for case in range(24):
+            block = int(rng.choice([8, 16]))
+            search = int(rng.choice([8, 16, 32]))
+            w = int(rng.integers(4, 60)) * 16
+            h = int(rng.integers(3, 40)) * 8
+            n = int(rng.integers(1, 4))
+            frames = synth.make_stream(n + 1, w, h, search, noise_lsb=int(rng.integers(0, 4)))
+            if rng.random() < 0.3:
+                frames[-1] = rng.integers(0, 256, frames[-1].shape, dtype=np.uint8)      # a cut: one pair goes to the work list
+            ctx.set_option("block_match_tile_h", int(rng.choice([0, 32, 64])))
+            a = ctx.block_match(frames[:-1], frames[1:], block, search, 0)
+            ctx.set_option("block_match_prune", 0)
+            b = ctx.block_match(frames[:-1], frames[1:], block, search, 0)
+            ctx.set_option("block_match_prune", 1)
+            for k in ("mv", "cost"):
+                np.testing.assert_array_equal(a[k], b[k], err_msg=f"case {case}: {w}x{h} b{block} r{search} n{n}")
+            assert a["entries"].tobytes() == b["entries"].tobytes()
+    finally:
+        ctx.set_option("block_match_prune", 1)
+        ctx.set_option("block_match_tile_h", 0)
+        ctx.set_option("block_match_adaptive", 1)
+
+
 def test_content_feedback_needs_two_bad_launches(ctx):
     """Content feedback of the SEA path (block_match_sea.cu): a launch that leaves most blocks to the exhaustive kernel
     is remembered; two in a row send the next 15 launches straight to the exhaustive kernel (1 kernel launch instead
